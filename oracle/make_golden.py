@@ -1,0 +1,307 @@
+"""TEST INFRASTRUCTURE ONLY — generates tests/golden/*.npz from the REAL reference.
+
+Run in the build container (where /root/reference is mounted):
+
+    python -m oracle.make_golden
+
+What it does
+  1. imports the reference's own VSMForCausalLM / visual_search (read-only,
+     through oracle/ref_shims.py) at the tiny golden config,
+  2. loads the deterministic synthetic weights (oracle.vsm_oracle.synthetic_state_dict)
+     into it,
+  3. runs the reference on seeded inputs and writes its outputs as golden
+     vectors,
+  4. asserts the CPU restatement (oracle/vsm_oracle.py) reproduces every one of
+     them (fp32: rtol 1e-4 / atol 1e-5; ids / argmax / trajectories identical).
+
+The goldens are what pins the oracle on the GPU box, where /root/reference
+does not exist.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import ref_shims, vsm_oracle as O  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def hf_cfgs(cfg: O.VSMConfig):
+    owl = dict(
+        vision_config=dict(hidden_size=cfg.owl_hidden, intermediate_size=cfg.owl_inter,
+                           num_hidden_layers=cfg.owl_layers, num_attention_heads=cfg.owl_heads,
+                           image_size=cfg.owl_image, patch_size=cfg.owl_patch, hidden_act="quick_gelu",
+                           layer_norm_eps=cfg.vit_eps),
+        text_config=dict(hidden_size=cfg.owl_query_dim, intermediate_size=128, num_hidden_layers=1,
+                         num_attention_heads=2, vocab_size=64, max_position_embeddings=16),
+        projection_dim=64)
+    clip = dict(hidden_size=cfg.clip_hidden, intermediate_size=cfg.clip_inter, num_hidden_layers=cfg.clip_layers,
+                num_attention_heads=cfg.clip_heads, image_size=cfg.clip_image, patch_size=cfg.clip_patch,
+                layer_norm_eps=cfg.vit_eps, hidden_act="quick_gelu", projection_dim=64)
+    return owl, clip
+
+
+def build_reference_model(cfg: O.VSMConfig, sd):
+    owl, clip = hf_cfgs(cfg)
+    ref_shims.install(owl, clip)
+    from VisualSearch.model.VSM import VSMForCausalLM
+    from VisualSearch.model.llava.model.language_model.llava_llama import LlavaConfig
+    lc = LlavaConfig(hidden_size=cfg.hidden, intermediate_size=cfg.intermediate, num_hidden_layers=cfg.n_layers,
+                     num_attention_heads=cfg.n_heads, num_key_value_heads=cfg.n_heads, vocab_size=cfg.vocab,
+                     rms_norm_eps=cfg.rms_eps, max_position_embeddings=2048, train_mask_decoder=True,
+                     out_dim=cfg.owl_query_dim, mm_vision_select_layer=cfg.clip_select_layer,
+                     mm_use_im_start_end=True, vision_tower="fake-clip", mm_vision_tower="fake-clip",
+                     mm_hidden_size=cfg.clip_hidden, attn_implementation="eager")
+    torch.manual_seed(0)
+    m = VSMForCausalLM(lc, loc_token_idx=cfg.loc_token_idx, is_eval=True)
+    m.get_model().initialize_vision_modules(m.get_model().config)
+    m.eval()
+    ref_keys = set(m.state_dict().keys())
+    missing_in_ref = [k for k in sd if k not in ref_keys]
+    assert not missing_in_ref, missing_in_ref
+    m.load_state_dict(sd, strict=False)
+    return m
+
+
+def synth_image(seed, w, h):
+    from PIL import Image
+    arr = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    return Image.fromarray(arr, "RGB")
+
+
+def ref_model_forward(m, images, images_clip, ids, size):
+    L = ids.shape[1]
+    with torch.no_grad():
+        return m.model_forward(images=images, images_clip=images_clip, input_ids=ids, labels=None,
+                               attention_masks=torch.ones(1, L, dtype=torch.long), offset=torch.tensor([0, 1]),
+                               masks_list=[None], label_list=[torch.zeros(*size)], bboxes_labels_list=[None],
+                               bboxes_valid_list=None, masks_valid_list=None, resize_list=[(768, 768)],
+                               inference=True)
+
+
+def close(a, b, name, rtol=1e-4, atol=2e-5):
+    a, b = torch.as_tensor(a).float(), torch.as_tensor(b).float()
+    err = (a - b).abs().max().item()
+    ok = torch.allclose(a, b, rtol=rtol, atol=atol)
+    print(f"  {name:28s} max|d|={err:.3e} ref|max|={b.abs().max().item():.3e} {'OK' if ok else 'MISMATCH'}")
+    assert ok, name
+
+
+def case_model_forward(m, sd, cfg, tag, img_seed, w, h, n_text):
+    print(f"[golden] model_forward case {tag}")
+    img = synth_image(img_seed, w, h)
+    images_clip = O.preprocess_clip(img)
+    images = O.preprocess_owl(img)
+    prompt, ans = O.synthetic_prompt(cfg, n_text=n_text, seed=img_seed)
+    ids = torch.cat([prompt, ans.unsqueeze(0)], dim=1)
+    ref = ref_model_forward(m, images, images_clip, ids, (h, w))
+    with torch.no_grad():
+        ref_lm = super(type(m), m).forward(images=images_clip, attention_mask=torch.ones_like(ids), input_ids=ids,
+                                            output_hidden_states=True)
+        ref_fmap = m.get_visual_embs(images)
+    orc = O.model_forward_inference(sd, cfg, images, images_clip, ids, (h, w))
+    close(orc["hidden"], ref_lm.hidden_states, "hidden")
+    close(orc["logits"], ref_lm.logits, "logits", atol=1e-4)
+    close(orc["feature_map"], ref_fmap, "owl feature_map")
+    close(orc["pred_masks"][0], ref["pred_masks"][0][0], "pred_mask", atol=1e-4)
+    close(orc["pred_logits"], ref["pred_logits"], "pred_logits", atol=1e-4)
+    close(orc["pred_boxes"], ref["pred_boxes"], "pred_boxes")
+    loc_row = int((ids[0] == cfg.loc_token_idx).nonzero()[0, 0]) - 1 + 255
+    pm = ref["pred_masks"][0][0]
+    g = dict(
+        img_seed=img_seed, w=w, h=h, input_ids=ids.numpy(),
+        loc_row=loc_row,
+        hidden_loc=ref_lm.hidden_states[0, loc_row].numpy(),
+        hidden_last=ref_lm.hidden_states[0, -1].numpy(),
+        logits_argmax=ref_lm.logits[0].argmax(-1).numpy(),
+        logits_last=ref_lm.logits[0, -1].numpy(),
+        fmap_sample=ref_fmap[0, ::6, ::6, :].numpy(),
+        seg_query=orc["seg_queries"].numpy(),     # oracle value (verified == reference downstream)
+        det_query=orc["det_queries"].numpy(),
+        low_res_mask=orc["low_res_masks"][0, 0].numpy(),
+        pred_mask_stats=np.array([pm.max().item(), pm.min().item(), pm.clamp(min=0).sum().item(),
+                                  float(pm.argmax())], dtype=np.float64),
+        pred_mask_sample=pm[::7, ::7].numpy(),
+        pred_logits=ref["pred_logits"][0, :, 0].numpy(),
+        pred_boxes=ref["pred_boxes"][0].numpy(),
+    )
+    np.savez_compressed(os.path.join(GOLDEN_DIR, f"model_forward_{tag}.npz"), **g)
+
+
+def case_generate(m, sd, cfg, tag, img_seed, w, h, n_text):
+    """Greedy loop restated around the REFERENCE forward (HF generate of the
+    reference's VSMForCausalLM.inference does not run under transformers 5.5,
+    SURVEY.md §8c)."""
+    print(f"[golden] generate case {tag}")
+    img = synth_image(img_seed, w, h)
+    images_clip = O.preprocess_clip(img)
+    prompt, ans = O.synthetic_prompt(cfg, n_text=n_text, seed=img_seed)
+    ids = prompt.clone()
+    ref_argmax, ref_last_logits = [], []
+    for step in range(len(ans)):
+        with torch.no_grad():
+            out = super(type(m), m).forward(images=images_clip, attention_mask=torch.ones_like(ids), input_ids=ids,
+                                             output_hidden_states=True)
+        ref_argmax.append(int(out.logits[0, -1].argmax()))
+        ref_last_logits.append(out.logits[0, -1].numpy().copy())
+        ids = torch.cat([ids, ans[step].view(1, 1)], dim=1)
+        if int(ans[step]) == 2:
+            break
+    o_ids, o_hidden, o_argmax = O.greedy_generate(sd, cfg, prompt, images_clip, max_new_tokens=100, eos_token_id=2,
+                                                  forced_ids=ans)
+    assert o_argmax == ref_argmax, (o_argmax, ref_argmax)
+    assert torch.equal(o_ids, ids)
+    close(o_hidden, out.hidden_states, "last-step hidden")
+    # free-running (unforced) greedy for a few tokens too
+    ids2 = prompt.clone()
+    free = []
+    for step in range(4):
+        with torch.no_grad():
+            out2 = super(type(m), m).forward(images=images_clip, attention_mask=torch.ones_like(ids2), input_ids=ids2)
+        t = int(out2.logits[0, -1].argmax())
+        free.append(t)
+        ids2 = torch.cat([ids2, torch.tensor([[t]])], dim=1)
+    o2_ids, _, o2_argmax = O.greedy_generate(sd, cfg, prompt, images_clip, max_new_tokens=4, eos_token_id=-1)
+    assert o2_argmax == free, (o2_argmax, free)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, f"generate_{tag}.npz"), img_seed=img_seed, w=w, h=h,
+                        prompt=prompt.numpy(), forced=ans.numpy(), argmax=np.array(ref_argmax),
+                        last_logits=np.stack(ref_last_logits), free_argmax=np.array(free),
+                        output_ids=ids.numpy(), hidden_loc=out.hidden_states[0, -3].numpy())
+
+
+# ---------------------------------------------------------------- search goldens
+class StubVSM:
+    """Deterministic stand-in for visual_search.VSM: outputs depend only on the
+    crop's pixels (so they are pure functions of the crop, like the real VSM)."""
+
+    def __init__(self, conf_peak_bbox=None, weak_every=0):
+        self.calls = []
+        self.weak_every = weak_every
+
+    def inference(self, image, question, mode="segmentation"):
+        arr = np.asarray(image, dtype=np.uint8)
+        h, w = arr.shape[:2]
+        self.calls.append((w, h, mode))
+        s = int(arr[::max(1, h // 16), ::max(1, w // 16)].astype(np.int64).sum()) % (2 ** 31)
+        rng = np.random.default_rng(s)
+        if mode == "vqa":
+            return "The object is most likely to appear near the table."
+        low = rng.standard_normal((12, 12)).astype(np.float32) * 4.0
+        hm = torch.nn.functional.interpolate(torch.from_numpy(low)[None, None], (h, w), mode="bilinear",
+                                             align_corners=False)[0, 0].clamp(min=0)
+        if mode == "segmentation":
+            return hm
+        logits = torch.from_numpy(rng.uniform(0.0, 0.45, (2304, 1)).astype(np.float32))
+        boxes = torch.from_numpy(rng.uniform(0.1, 0.9, (2304, 4)).astype(np.float32))
+        return boxes, logits, hm
+
+
+def trajectory(search_path):
+    return np.array([st["bbox"] for st in search_path], dtype=np.int64)
+
+
+def case_search(tag, img_seed, w, h, smallest, **kw):
+    print(f"[golden] search case {tag}")
+    import visual_search as RVS  # the reference module
+    img = synth_image(img_seed, w, h)
+    stub = StubVSM()
+    fs, pl, ok, av = RVS.visual_search(stub, img, "mug", None, smallest, **kw)
+    ref_calls = list(stub.calls)
+    stub2 = StubVSM()
+    fs2, pl2, ok2, av2, path2 = O.visual_search(stub2, img, "mug", None, smallest, **kw)
+    assert ref_calls == stub2.calls
+    assert pl == pl2 and ok == ok2 and fs["bbox"] == fs2["bbox"]
+    assert torch.equal(fs["detection_result"], fs2["detection_result"])
+    np.savez_compressed(os.path.join(GOLDEN_DIR, f"search_{tag}.npz"), img_seed=img_seed, w=w, h=h, smallest=smallest,
+                        kw=json.dumps(kw), calls=np.array([(c[0], c[1], {"detection": 0, "vqa": 1, "segmentation": 2}[c[2]])
+                                                           for c in ref_calls], dtype=np.int64),
+                        trajectory=trajectory(path2), path_length=pl, success=int(ok), final_bbox=np.array(fs["bbox"]),
+                        detection_result=fs["detection_result"].numpy())
+    print(f"   {len(ref_calls)} VSM calls, path_length={pl}, success={ok}")
+
+
+class RefModelVSM:
+    """visual_search.VSM-shaped wrapper around the REFERENCE model graph with
+    teacher-forced ids (no tokenizer offline): used to pin an end-to-end
+    trajectory produced by reference search loop x reference model."""
+
+    def __init__(self, m, cfg):
+        self.m, self.cfg = m, cfg
+        prompt, ans = O.synthetic_prompt(cfg, n_text=24, seed=5)
+        self.ids = torch.cat([prompt, ans.unsqueeze(0)], dim=1)
+        self.calls = 0
+
+    def inference(self, image, question, mode="segmentation"):
+        self.calls += 1
+        images_clip = O.preprocess_clip(image)
+        images = O.preprocess_owl(image)
+        out = ref_model_forward(self.m, images, images_clip, self.ids, (image.height, image.width))
+        pm = torch.clamp(out["pred_masks"][0], min=0)[-1]
+        if mode == "segmentation":
+            return pm
+        return out["pred_boxes"][0], out["pred_logits"][0].sigmoid(), pm
+
+
+class OracleVSM:
+    def __init__(self, sd, cfg):
+        self.sd, self.cfg = sd, cfg
+        prompt, ans = O.synthetic_prompt(cfg, n_text=24, seed=5)
+        self.ids = torch.cat([prompt, ans.unsqueeze(0)], dim=1)
+
+    def inference(self, image, question, mode="segmentation"):
+        out = O.model_forward_inference(self.sd, self.cfg, O.preprocess_owl(image), O.preprocess_clip(image), self.ids,
+                                        (image.height, image.width))
+        pm = torch.clamp(out["pred_masks"], min=0)[-1]
+        if mode == "segmentation":
+            return pm
+        return out["pred_boxes"][0], out["pred_logits"][0].sigmoid(), pm
+
+
+def case_search_model(m, sd, cfg, tag, img_seed, w, h, smallest, **kw):
+    print(f"[golden] search+model case {tag}")
+    import visual_search as RVS
+    img = synth_image(img_seed, w, h)
+    with torch.no_grad():
+        fs, pl, ok, av = RVS.visual_search(RefModelVSM(m, cfg), img, "mug", None, smallest, **kw)
+        fs2, pl2, ok2, av2, path2 = O.visual_search(OracleVSM(sd, cfg), img, "mug", None, smallest, **kw)
+    assert pl == pl2 and ok == ok2 and fs["bbox"] == fs2["bbox"], (pl, pl2, fs["bbox"], fs2["bbox"])
+    close(fs2["detection_result"], fs["detection_result"], "final detection_result", atol=1e-2)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, f"search_model_{tag}.npz"), img_seed=img_seed, w=w, h=h,
+                        smallest=smallest, kw=json.dumps(kw), trajectory=trajectory(path2), path_length=pl,
+                        success=int(ok), final_bbox=np.array(fs["bbox"]),
+                        detection_result=fs["detection_result"].numpy(),
+                        scores=np.array([st["score"] if st["score"] is not None else np.nan for st in path2], dtype=np.float64))
+    print(f"   path_length={pl}, success={ok}, nodes={len(path2)}")
+
+
+def main():
+    assert ref_shims.reference_available(), "needs /root/reference (build container only)"
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.set_num_threads(8)
+    cfg = O.tiny_config()
+    sd = O.synthetic_state_dict(cfg, seed=1234)
+    m = build_reference_model(cfg, sd)
+    with open(os.path.join(GOLDEN_DIR, "tiny_config.json"), "w") as f:
+        json.dump(dict(cfg=cfg.to_dict(), weight_seed=1234), f, indent=1)
+    case_model_forward(m, sd, cfg, "a", img_seed=11, w=150, h=110, n_text=24)
+    case_model_forward(m, sd, cfg, "b", img_seed=12, w=96, h=233, n_text=60)
+    case_generate(m, sd, cfg, "a", img_seed=13, w=128, h=128, n_text=24)
+    case_search("stub_3lvl", img_seed=21, w=1024, h=1024, smallest=224, confidence_high=2.0)
+    case_search("stub_default", img_seed=22, w=1500, h=700, smallest=224)
+    case_search("stub_weakcue", img_seed=23, w=900, h=1900, smallest=300, confidence_high=2.0,
+                target_cue_threshold=50.0, target_cue_threshold_minimum=40.0)
+    case_search_model(m, sd, cfg, "a", img_seed=31, w=640, h=512, smallest=200, confidence_high=2.0,
+                      target_cue_threshold=-1e9, target_cue_threshold_minimum=-1e9)
+    print("golden vectors written to", GOLDEN_DIR)
+
+
+if __name__ == "__main__":
+    main()
