@@ -1,0 +1,103 @@
+/* vstar_b200 C-ABI — the drop-in boundary of the B200-native V* (SEAL) visual-search hot path.
+ *
+ * The reference (penghao-wu/vstar) is pure Python and has no FFI layer of its own: the boundary it
+ * exposes is the Python API of visual_search.py / VSM.py, mirrored by the host code in
+ * vstar_b200/.  Underneath that mirror every arithmetic op of the path is one of the entry points
+ * below: plain C, raw DEVICE pointers + sizes + a cudaStream_t passed as void*, no torch types, no
+ * allocation inside, no global state except a TMA-descriptor cache.  Each entry point cites the
+ * reference op site(s) (file:line) it replaces.
+ *
+ * Return value: 0 on success, negative on error (VSB_ERR_*); vsb_last_error() gives the message.
+ * All matrices are row-major; "ld*" are leading dimensions in ELEMENTS; bf16 = __nv_bfloat16.
+ */
+#ifndef VSTAR_B200_H_
+#define VSTAR_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSB_EPI_NONE 0
+#define VSB_EPI_QUICK_GELU 1 /* x*sigmoid(1.702x): CLIP / OWL-ViT MLP (transformers/activations.py:117-123) */
+#define VSB_EPI_GELU 2       /* exact erf GELU: OWL box head, SAM upscaling */
+#define VSB_EPI_RELU 3       /* SAM transformer MLP, text_hidden_fcs, hyper-network MLPs */
+#define VSB_EPI_SWIGLU 4     /* silu(gate)*up with gate/up rows interleaved in W (Llama MLP) */
+
+#define VSB_HEATMAP_MAX_BLOCKS 1184 /* 148 SMs x 8 */
+
+const char* vsb_last_error(void);
+int vsb_version(void);
+
+/* C[M,N] = epi(A[M,K] . W[N,K]^T + bias[N]) (+ residual[M,N]); tcgen05/TMEM/TMA GEMM, bf16 operands, fp32
+ * accumulate.  out_fp32: C/residual element type (0 = bf16, 1 = fp32).  Output-row remap (rows_per_group > 0):
+ * row m -> (m / rows_per_group) * group_stride + group_offset + m % rows_per_group (used to scatter the 256
+ * projected CLIP rows of each crop straight into the LLM input buffer; llava_arch.py:185-208).
+ * Replaces every nn.Linear / conv-as-GEMM on the path:
+ *   VisualSearch/model/llava/model/llava_arch.py:93-96 (mm_projector); HF LlamaModel q/k/v/o/gate/up/down and
+ *   lm_head via llava_llama.py:93-105; HF CLIP/OWL-ViT patch-embed + encoder linears via clip_encoder.py:53-57
+ *   and owlvit.py:121-126; VSM.py:117-140 (text_hidden_fcs), :88 (visual_projection); owlvit.py:79-119 heads;
+ *   segment_anything/modeling/transformer.py:205-242, mask_decoder.py:15-27,:191-213. */
+int vsb_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
+                  const void* bias, const void* residual, long long ldr, int epilogue, int out_fp32, int rows_per_group,
+                  long long group_stride, long long group_offset, void* stream);
+/* testing / tuning hook: force tile width (64/128/256, 0 = auto) and CTA count (0 = #SMs) */
+int vsb_gemm_set_tuning(int force_bn, int max_ctas);
+
+/* nn.LayerNorm over the last dim (fp32 stats), optional fused activation (VSB_EPI_NONE / VSB_EPI_GELU).
+ * HF CLIP/OWL layer_norm1/2, pre/post layernorm; SAM norm1-4, norm_final_attn; LayerNorm2d in NHWC (common.py:31-43). */
+int vsb_layernorm_bf16(const void* x, long long ldx, const void* w, const void* b, void* y, long long ldy, int rows, int cols,
+                       float eps, int act, void* stream);
+/* HF LlamaRMSNorm (transformers/models/llama/modeling_llama.py:53-67): y = w * bf16(x * rsqrt(mean(x^2)+eps)). */
+int vsb_rmsnorm_bf16(const void* x, long long ldx, const void* w, void* y, long long ldy, int rows, int cols, float eps, void* stream);
+/* rotate-half RoPE in place on the q and k thirds of a fused qkv buffer [.., 3*H*D]
+ * (modeling_llama.py:117-168); cos/sin tables bf16 [max_pos, D/2]; position = positions[r] or pos0 + r % T;
+ * logical row r is stored at physical row (r / T) * group_stride + group_offset + r % T (KV-cache layout). */
+int vsb_rope_bf16(void* qkv, long long ld, int rows, int T, int H, int D, int pos0, const void* cos_table, const void* sin_table,
+                  const void* positions, long long group_stride, long long group_offset, void* stream);
+/* embed_tokens lookup for the text slots of the spliced sequence (llava_arch.py:185-208, :235-251);
+ * ids int64 [B,L] with the image placeholder at img_pos; out [B, L-1+n_img, d]. */
+int vsb_embed_splice_bf16(const void* ids, const void* table, void* out, int B, int L, int img_pos, int n_img, int d, int vocab, void* stream);
+int vsb_gather_rows_bf16(const void* idx_i64, const void* table, long long ldt, void* out, long long ldo, int n, int d,
+                         long long nrows_table, void* stream);
+/* im2col for the stride==kernel patch-embedding conv (HF CLIPVisionEmbeddings / OwlViTVisionEmbeddings). */
+int vsb_patchify_bf16(const void* pixels, void* A, int B, int S, int P, int Kpad, void* stream);
+/* x[:,0] = cls + pos[0]; x[:,1:] += pos[1:] */
+int vsb_vit_add_pos_bf16(void* x, const void* cls, const void* pos, int B, int S, int C, void* stream);
+/* OwlViT.get_visual_embs tail (owlvit.py:128-138): LN2(LN1(x[:,1:]) * LN1(x[:,:1])). */
+int vsb_owl_merge_bf16(const void* x, const void* w1, const void* b1, const void* w2, const void* b2, void* y, int B, int S, int C,
+                       float eps, void* stream);
+int vsb_add_rows_bf16(const void* a, const void* b, void* y, long long rows, int cols, long long bmod, void* stream);
+int vsb_cast_f32_bf16(const void* x, void* y, long long n, void* stream);
+int vsb_argmax_rows_f32(const void* x, long long ld, int rows, int n, void* idx_i32, void* val_f32, void* stream);
+int vsb_copy2d_b16(const void* src, long long lds, void* dst, long long ldd, long long rows, int cols, void* stream);
+
+/* softmax(QK^T*scale [+causal]) V, head_dim 64/128; element (b,s,h,d) at base + b*bs + s*rs + h*D + d.
+ * HF CLIP/OWL attention (modeling_clip.py:261-329) and Llama attention (modeling_llama.py:199-221). */
+int vsb_flash_attn_bf16(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_rs, long long k_bs,
+                        long long k_rs, long long v_bs, long long v_rs, long long o_bs, long long o_rs, int B, int H, int Sq, int Sk,
+                        int D, int causal, float scale, void* stream);
+/* SAM two-way transformer attention, head_dim 16/32 (segment_anything/modeling/transformer.py:220-242). */
+int vsb_attn_small_bf16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
+                        int B, int H, int Nq, int Nk, int D, float scale, void* stream);
+
+/* OWL-ViT class head epilogue on y = [dense0(x) | logit_shift(x) | logit_scale(x)] (fp32) and box head epilogue
+ * (modeling_owlvit.py:1043-1062; owlvit.py:63-100). */
+int vsb_owl_class_post(const void* y, long long ldy, const void* query, long long ldq, int rows_per_crop, long long R, int Q, void* logits,
+                       void* scores, void* stream);
+int vsb_owl_box_post(const void* y, long long ldy, const void* box_bias, int rows_per_crop, long long R, void* boxes, void* stream);
+
+/* SAM mask-decoder upscaling helpers (mask_decoder.py:15-27, :78-84, :169-181), channels-last. */
+int vsb_upsample2x_nhwc_bf16(const void* x, void* y, int B, int H, int W, int C, void* stream);
+int vsb_im2col3x3_nhwc_bf16(const void* x, void* A, int B, int H, int W, int C, void* stream);
+int vsb_mask_dot_bf16(const void* up, const void* hyper, void* out, int B, long long P, int C, void* stream);
+
+/* target-cue heatmap: bilinear(align_corners=False) of the fp32 low-res mask to (h,w), optional clamp(min=0),
+ * plus (max,min,sum) (VSM.py:534-537; visual_search.py:223-224, :268-275, :420-421). */
+int vsb_heatmap_bilinear_f32(const void* low, int LH, int LW, void* out, int h, int w, int do_clamp, void* scratch, void* stats3, void* stream);
+/* sums of the min-max-normalised heatmap over integer rectangles [x,y,w,h] (visual_search.py:255-266). */
+int vsb_rect_sums_f32(const void* hm, int h, int w, const void* rects_i32, int nrects, const void* stats3, void* out_f64, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSTAR_B200_H_ */

@@ -1,0 +1,314 @@
+"""Per-kernel parity on a real B200: every C-ABI entry point against the same op in plain PyTorch
+(fp32 math on the same bf16-rounded inputs).  Tolerances are written per test."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from vstar_b200 import ops as o
+    return o
+
+
+def rnd(*shape, scale=1.0, seed=0, dtype=BF):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).cuda()
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+GEMM_SHAPES = [
+    (128, 128, 64), (128, 256, 128), (256, 512, 256), (1, 128, 64), (5, 4, 768), (257, 1024, 1024),
+    (300, 514, 768), (640, 11008, 512), (2304, 768, 768), (320, 4096, 4096), (77, 200, 592), (128, 64, 2304),
+    (1280, 8192, 1024),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_plain(ops, M, N, K):
+    a, w = rnd(M, K, seed=1), rnd(N, K, scale=1 / math.sqrt(K), seed=2)
+    out = ops.gemm(a, w)
+    ref = a.float() @ w.float().t()
+    torch.cuda.synchronize()
+    assert out.shape == (M, N)
+    # bf16 output rounding: rel 2^-8 of the value + fp32 accumulation noise
+    assert torch.allclose(out.float(), ref, rtol=1e-2, atol=2e-2), rel_err(out, ref)
+
+
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_gemm_forced_tile(ops, bn):
+    from vstar_b200 import _lib
+    M, N, K = 384, 768, 320
+    a, w = rnd(M, K, seed=3), rnd(N, K, scale=1 / math.sqrt(K), seed=4)
+    _lib.call("vsb_gemm_set_tuning", bn, 0)
+    try:
+        out = ops.gemm(a, w, out_dtype=torch.float32)
+    finally:
+        _lib.call("vsb_gemm_set_tuning", 0, 0)
+    ref = a.float() @ w.float().t()
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-3), rel_err(out, ref)
+
+
+def test_gemm_persistent_many_tiles(ops):
+    """few CTAs, many tiles per CTA: exercises the smem ring phases and the TMEM double buffer"""
+    from vstar_b200 import _lib
+    M, N, K = 1024, 1536, 448
+    a, w = rnd(M, K, seed=5), rnd(N, K, scale=1 / math.sqrt(K), seed=6)
+    _lib.call("vsb_gemm_set_tuning", 128, 3)
+    try:
+        out = ops.gemm(a, w, out_dtype=torch.float32)
+    finally:
+        _lib.call("vsb_gemm_set_tuning", 0, 0)
+    ref = a.float() @ w.float().t()
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-3), rel_err(out, ref)
+
+
+@pytest.mark.parametrize("epi", ["none", "quick_gelu", "gelu", "relu"])
+def test_gemm_bias_act_residual(ops, epi):
+    M, N, K = 515, 1000, 256
+    a, w, b, r = rnd(M, K, seed=7), rnd(N, K, scale=1 / math.sqrt(K), seed=8), rnd(N, seed=9), rnd(M, N, seed=10)
+    code = dict(none=ops.EPI_NONE, quick_gelu=ops.EPI_QUICK_GELU, gelu=ops.EPI_GELU, relu=ops.EPI_RELU)[epi]
+    out = ops.gemm(a, w, bias=b, residual=r, epilogue=code)
+    y = a.float() @ w.float().t() + b.float()
+    y = dict(none=lambda t: t, quick_gelu=lambda t: t * torch.sigmoid(1.702 * t), gelu=F.gelu, relu=F.relu)[epi](y)
+    ref = y + r.float()
+    assert torch.allclose(out.float(), ref, rtol=1e-2, atol=3e-2), rel_err(out, ref)
+
+
+def test_gemm_swiglu(ops):
+    M, I, K = 200, 704, 256
+    a = rnd(M, K, seed=11)
+    gate, up = rnd(I, K, scale=1 / math.sqrt(K), seed=12), rnd(I, K, scale=1 / math.sqrt(K), seed=13)
+    w = torch.stack([gate, up], dim=1).reshape(2 * I, K).contiguous()     # interleaved rows
+    out = ops.gemm(a, w, epilogue=ops.EPI_SWIGLU)
+    ref = F.silu(a.float() @ gate.float().t()) * (a.float() @ up.float().t())
+    assert out.shape == (M, I)
+    assert torch.allclose(out.float(), ref, rtol=1e-2, atol=2e-2), rel_err(out, ref)
+
+
+def test_gemm_row_remap_and_strided(ops):
+    """scatter 256-row groups into a [B, T, d] buffer at offset p (the mm_projector -> LLM input path)"""
+    B, G, K, N, T, p0 = 3, 256, 128, 512, 300, 20
+    a, w, b = rnd(B * G, K, seed=14), rnd(N, K, scale=1 / math.sqrt(K), seed=15), rnd(N, seed=16)
+    buf = torch.zeros(B * T, N, dtype=BF, device="cuda")
+    ops.gemm(a, w, out=buf, bias=b, rows_per_group=G, group_stride=T, group_offset=p0)
+    ref = (a.float() @ w.float().t() + b.float()).view(B, G, N)
+    got = buf.view(B, T, N)
+    assert torch.allclose(got[:, p0:p0 + G].float(), ref, rtol=1e-2, atol=2e-2)
+    assert float(got[:, :p0].abs().max()) == 0 and float(got[:, p0 + G:].abs().max()) == 0
+    # strided A (a column slice of a wider matrix) and strided output
+    wide = rnd(100, 3 * K, seed=17)
+    o2 = torch.zeros(100, 2 * N, dtype=BF, device="cuda")
+    ops.gemm(wide[:, K:2 * K], w, out=o2[:, N:])
+    assert torch.allclose(o2[:, N:].float(), wide[:, K:2 * K].float() @ w.float().t(), rtol=1e-2, atol=2e-2)
+    assert float(o2[:, :N].abs().max()) == 0
+
+
+def test_layernorm_rmsnorm(ops):
+    for rows, cols in [(7, 64), (300, 768), (257, 1024), (33, 4096), (10, 256)]:
+        x, w, b = rnd(rows, cols, seed=20), (1 + 0.1 * torch.randn(cols)).to(BF).cuda(), rnd(cols, scale=0.1, seed=21)
+        y = ops.layernorm(x, w, b, 1e-5)
+        ref = F.layer_norm(x.float(), (cols,), w.float(), b.float(), 1e-5)
+        assert torch.allclose(y.float(), ref, rtol=1e-2, atol=1e-2), (rows, cols, rel_err(y, ref))
+        y = ops.layernorm(x, w, b, 1e-6, act=ops.EPI_GELU)
+        assert torch.allclose(y.float(), F.gelu(F.layer_norm(x.float(), (cols,), w.float(), b.float(), 1e-6)), rtol=1e-2, atol=1e-2)
+        z = ops.rmsnorm(x, w, 1e-6)
+        xf = x.float()
+        refz = w.float() * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)).to(BF).float()
+        assert torch.allclose(z.float(), refz, rtol=1e-2, atol=1e-2), (rows, cols, rel_err(z, refz))
+
+
+def _rope_tables(maxpos, D, theta=10000.0):
+    inv = 1.0 / (theta ** (torch.arange(0, D, 2, dtype=torch.float32) / D))
+    fr = torch.outer(torch.arange(maxpos, dtype=torch.float32), inv)
+    return fr.cos().to(BF).cuda(), fr.sin().to(BF).cuda()
+
+
+def test_rope_bit_exact(ops):
+    B, T, H, D = 2, 37, 3, 128
+    qkv = rnd(B * T, 3 * H * D, seed=30)
+    cos_t, sin_t = _rope_tables(64, D)
+    ref = qkv.clone().view(B, T, 3, H, D)
+    cos = torch.cat([cos_t[:T], cos_t[:T]], -1)[None, :, None, :]
+    sin = torch.cat([sin_t[:T], sin_t[:T]], -1)[None, :, None, :]
+
+    def rot(x):
+        return torch.cat([-x[..., D // 2:], x[..., :D // 2]], -1)
+
+    for i in (0, 1):
+        x = ref[:, :, i]
+        ref[:, :, i] = (x * cos) + (rot(x) * sin)          # bf16 ops, like HF
+    out = ops.rope_(qkv.clone(), T, H, D, cos_t, sin_t)
+    assert torch.equal(out.view(B, T, 3, H, D), ref)
+    # explicit positions (decode step)
+    pos = torch.full((B * T,), 41, dtype=torch.int32, device="cuda")
+    out2 = ops.rope_(qkv.clone(), T, H, D, cos_t, sin_t, positions=pos).view(B, T, 3, H, D)
+    c41 = torch.cat([cos_t[41], cos_t[41]])
+    s41 = torch.cat([sin_t[41], sin_t[41]])
+    x = qkv.view(B, T, 3, H, D)[:, :, 0]
+    assert torch.equal(out2[:, :, 0], (x * c41) + (rot(x) * s41))
+    assert torch.equal(out2[:, :, 2], qkv.view(B, T, 3, H, D)[:, :, 2])
+
+
+@pytest.mark.parametrize("B,H,S,D,causal", [(1, 2, 257, 64, False), (2, 3, 2305, 64, False), (2, 4, 320, 128, True),
+                                            (1, 2, 64, 128, True), (3, 2, 1, 128, False), (1, 1, 130, 64, True)])
+def test_flash_attn(ops, B, H, S, D, causal):
+    qkv = rnd(B * S, 3 * H * D, seed=40)
+    out = ops.attn_fused_qkv(qkv, B, S, H, D, causal, D ** -0.5)
+    q, k, v = [t.transpose(1, 2).float() for t in qkv.view(B, S, 3, H, D).unbind(2)]
+    att = q @ k.transpose(-1, -2) * D ** -0.5
+    if causal:
+        att = att + torch.full((S, S), float("-inf"), device="cuda").triu(1)
+    ref = (torch.softmax(att, -1) @ v).transpose(1, 2).reshape(B * S, H * D)
+    assert torch.allclose(out.float(), ref, rtol=2e-2, atol=2e-2), rel_err(out, ref)
+
+
+def test_flash_attn_kv_cache_decode(ops):
+    """Sq < Sk with causal offset (decode step against a KV cache with a different row stride)"""
+    B, H, D, Sk, Sq, Tmax = 2, 4, 128, 100, 3, 128
+    q = rnd(B * Sq, H * D, seed=41)
+    kc, vc = rnd(B, Tmax, H * D, seed=42), rnd(B, Tmax, H * D, seed=43)
+    out = torch.empty(B * Sq, H * D, dtype=BF, device="cuda")
+    ops.flash_attn(q, kc, vc, out, B, H, Sq, Sk, D, True, D ** -0.5, Sq * H * D, H * D, Tmax * H * D, H * D, Tmax * H * D, H * D,
+                   Sq * H * D, H * D)
+    qf = q.view(B, Sq, H, D).transpose(1, 2).float()
+    kf = kc[:, :Sk].view(B, Sk, H, D).transpose(1, 2).float()
+    vf = vc[:, :Sk].view(B, Sk, H, D).transpose(1, 2).float()
+    att = qf @ kf.transpose(-1, -2) * D ** -0.5
+    mask = torch.ones(Sq, Sk, device="cuda").tril(Sk - Sq).bool()
+    att = att.masked_fill(~mask, float("-inf"))
+    ref = (torch.softmax(att, -1) @ vf).transpose(1, 2).reshape(B * Sq, H * D)
+    assert torch.allclose(out.float(), ref, rtol=2e-2, atol=2e-2), rel_err(out, ref)
+
+
+@pytest.mark.parametrize("Nq,Nk,D", [(6, 2304, 16), (2304, 6, 16), (6, 6, 32)])
+def test_attn_small(ops, Nq, Nk, D):
+    B, H = 2, 8
+    q, k, v = rnd(B * Nq, H * D, seed=50), rnd(B * Nk, H * D, seed=51), rnd(B * Nk, H * D, seed=52)
+    out = ops.attn_small(q, k, v, B, H, Nq, Nk, D, 1 / math.sqrt(D))
+    qf = q.view(B, Nq, H, D).transpose(1, 2).float()
+    kf = k.view(B, Nk, H, D).transpose(1, 2).float()
+    vf = v.view(B, Nk, H, D).transpose(1, 2).float()
+    ref = (torch.softmax(qf @ kf.transpose(-1, -2) / math.sqrt(D), -1) @ vf).transpose(1, 2).reshape(B * Nq, H * D)
+    assert torch.allclose(out.float(), ref, rtol=1e-2, atol=1e-2), rel_err(out, ref)
+
+
+def test_embed_splice_gather_patchify_pos(ops):
+    V, d, B, L, img_pos, n_img = 500, 256, 2, 20, 7, 16
+    table = rnd(V, d, seed=60)
+    ids = torch.randint(0, V, (B, L), device="cuda")
+    ids[:, img_pos] = -200
+    T = L - 1 + n_img
+    out = torch.zeros(B, T, d, dtype=BF, device="cuda")
+    ops.embed_splice(ids, table, out, img_pos, n_img)
+    for b in range(B):
+        assert torch.equal(out[b, :img_pos], table[ids[b, :img_pos]])
+        assert torch.equal(out[b, img_pos + n_img:], table[ids[b, img_pos + 1:]])
+        assert float(out[b, img_pos:img_pos + n_img].abs().max()) == 0
+    idx = torch.tensor([3, 499, 0, 17], device="cuda")
+    assert torch.equal(ops.gather_rows(idx, table), table[idx])
+    # patchify == unfold with (c, py, px) ordering == conv weight.view(C_out, -1)
+    Bi, S, P = 2, 56, 14
+    px = rnd(Bi, 3, S, S, seed=61)
+    A = ops.patchify(px, P, 592)
+    ref = F.unfold(px.float(), kernel_size=P, stride=P).transpose(1, 2).reshape(-1, 3 * P * P)
+    assert torch.equal(A[:, :588].float(), ref) and float(A[:, 588:].abs().max()) == 0
+    x = rnd(Bi * 17, 64, seed=62)
+    cls, pos = rnd(64, seed=63), rnd(17, 64, seed=64)
+    y = ops.vit_add_pos_(x.clone(), cls, pos, Bi, 17).view(Bi, 17, 64)
+    refy = torch.cat([cls.expand(Bi, 1, 64), x.view(Bi, 17, 64)[:, 1:]], 1) + pos
+    assert torch.equal(y, refy)
+
+
+def test_owl_merge_and_heads(ops):
+    B, S, C, Q = 2, 2305, 128, 64
+    x = rnd(B * S, C, seed=70)
+    w1, b1, w2, b2 = [(1 + 0.1 * torch.randn(C)).to(BF).cuda() if i % 2 == 0 else rnd(C, scale=0.1, seed=71 + i) for i in range(4)]
+    y = ops.owl_merge(x, w1, b1, w2, b2, B, S, 1e-5)
+    xe = F.layer_norm(x.float().view(B, S, C), (C,), w1.float(), b1.float(), 1e-5).to(BF)
+    m = (xe[:, 1:] * xe[:, :1])
+    ref = F.layer_norm(m.float(), (C,), w2.float(), b2.float(), 1e-5)
+    assert torch.allclose(y.view(B, S - 1, C).float(), ref, rtol=2e-2, atol=2e-2), rel_err(y.view(B, S - 1, C), ref)
+    # class head epilogue
+    R = B * 2304
+    yy = torch.randn(R, Q + 2, device="cuda")
+    query = rnd(B, Q, seed=75)
+    logits, scores = ops.owl_class_post(yy, query, 2304, Q)
+    e = yy[:, :Q].view(B, 2304, Q)
+    e = e / (e.norm(dim=-1, keepdim=True) + 1e-6)
+    qn = query.float() / (query.float().norm(dim=-1, keepdim=True) + 1e-6)
+    lg = (torch.einsum("bpd,bd->bp", e, qn) + yy[:, Q].view(B, 2304)) * (F.elu(yy[:, Q + 1].view(B, 2304)) + 1)
+    assert torch.allclose(logits.view(B, 2304), lg, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(scores.view(B, 2304), torch.sigmoid(lg), rtol=1e-4, atol=1e-5)
+    bias = torch.randn(2304, 4, device="cuda")
+    yb = torch.randn(R, 4, device="cuda")
+    boxes = ops.owl_box_post(yb, bias, 2304)
+    assert torch.allclose(boxes.view(B, 2304, 4), torch.sigmoid(yb.view(B, 2304, 4) + bias), rtol=1e-5, atol=1e-6)
+    idx, val = ops.argmax_rows(logits.view(B, 2304))
+    assert torch.equal(idx.long(), logits.view(B, 2304).argmax(-1))
+
+
+def test_sam_upscale_helpers(ops):
+    B, H, W, C = 2, 12, 12, 64
+    x = rnd(B * H * W, C, seed=80)
+    up = ops.upsample2x_nhwc(x, B, H, W, C)
+    nchw = x.view(B, H, W, C).permute(0, 3, 1, 2).float()
+    ref = F.interpolate(nchw, scale_factor=2.0, mode="bilinear").to(BF).permute(0, 2, 3, 1).reshape(-1, C)
+    assert torch.equal(up, ref)
+    A = ops.im2col3x3_nhwc(up, B, 2 * H, 2 * W, C)
+    wconv = rnd(32, C, 3, 3, scale=0.05, seed=81)
+    wperm = wconv.permute(0, 2, 3, 1).reshape(32, 9 * C).contiguous()
+    out = ops.gemm(A, wperm, out_dtype=torch.float32)
+    refc = F.conv2d(up.view(B, 2 * H, 2 * W, C).permute(0, 3, 1, 2).float(), wconv.float(), padding=1).permute(0, 2, 3, 1).reshape(-1, 32)
+    assert torch.allclose(out, refc, rtol=1e-3, atol=1e-3), rel_err(out, refc)
+    hyper = rnd(B, 32, seed=82)
+    upb = out.to(BF).contiguous()
+    md = ops.mask_dot(upb, hyper, B, 4 * H * W, 32)
+    refm = torch.einsum("bpc,bc->bp", upb.view(B, -1, 32).float(), hyper.float())
+    assert torch.allclose(md, refm, rtol=1e-4, atol=1e-4)
+    a, bb = rnd(B * 10, 64, seed=83), rnd(10, 64, seed=84)
+    assert torch.equal(ops.add_rows(a, bb).view(B, 10, 64), a.view(B, 10, 64) + bb)
+
+
+@pytest.mark.parametrize("h,w", [(100, 120), (233, 96), (768, 768), (1023, 517), (2048, 2048)])
+def test_heatmap_and_rect_sums(ops, h, w):
+    low = torch.randn(192, 192, device="cuda") * 3
+    hm, stats = ops.heatmap(low, h, w)
+    ref = F.interpolate(low[None, None], (h, w), mode="bilinear", align_corners=False)[0, 0].clamp(min=0)
+    assert torch.allclose(hm, ref, rtol=1e-5, atol=1e-5), rel_err(hm, ref)
+    s = stats.cpu()
+    assert abs(float(s[0]) - float(hm.max())) < 1e-6 and abs(float(s[1]) - float(hm.min())) < 1e-6
+    assert abs(float(s[2]) - float(hm.double().sum())) <= 1e-5 * float(hm.double().sum()) + 1e-3
+    rects = torch.tensor([[0, 0, w // 2, h // 2], [w // 2, 0, w - w // 2, h // 2], [0, h // 2, w // 2, h - h // 2],
+                          [w // 2, h // 2, w - w // 2, h - h // 2], [0, 0, w, h], [3, 5, 1, 1]], dtype=torch.int32, device="cuda")
+    sums = ops.rect_sums(hm, rects, stats).cpu()
+    norm = ((hm - hm.min()) / (hm.max() - hm.min())).double()
+    for i, (x0, y0, rw, rh) in enumerate(rects.cpu().tolist()):
+        want = float(norm[y0:y0 + rh, x0:x0 + rw].sum())
+        assert abs(float(sums[i]) - want) <= 1e-5 * abs(want) + 1e-4, (i, float(sums[i]), want)
+
+
+def test_copy2d_and_cast(ops):
+    src = rnd(50, 3 * 128, seed=90)
+    dst = torch.zeros(50, 2 * 128, dtype=BF, device="cuda")
+    ops.copy2d(src[:, 128:256], dst[:, 128:])
+    assert torch.equal(dst[:, 128:], src[:, 128:256]) and float(dst[:, :128].abs().max()) == 0
+    x = torch.randn(1000, device="cuda")
+    assert torch.equal(ops.cast_f32_bf16(x), x.to(BF))
+
+
+def test_ops_fail_loudly_on_cpu_tensors(ops):
+    from vstar_b200._lib import VsbError
+    with pytest.raises(VsbError):
+        ops.gemm(torch.zeros(8, 8, dtype=BF), torch.zeros(8, 8, dtype=BF))

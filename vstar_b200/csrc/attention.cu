@@ -1,0 +1,344 @@
+// Attention kernels.
+//
+//  vsb_flash_attn_bf16  : softmax(Q K^T * scale [+ causal]) V for head_dim 64 / 128, bf16 in/out, fp32
+//                         online softmax.  Used by CLIP-L/14 (S=257, 16 heads x 64), OWL-ViT-B/16 (S=2305,
+//                         12 x 64) and the 7B prefill/decode (32 x 128, causal, KV cache).  Reference op
+//                         sites H2/H5/H10: transformers/models/clip/modeling_clip.py:261-329,
+//                         transformers/models/llama/modeling_llama.py:199-221 (softmax in fp32, P cast to bf16).
+//                         Round-1 implementation: FA2-style tiling (64 queries x 64 keys per step, cp.async
+//                         double-buffered K/V in XOR-swizzled shared memory, ldmatrix + mma.sync.m16n8k16).
+//                         A tcgen05/TMEM version replaces this in a later round; attention is ~5 % of the
+//                         per-crop FLOPs.
+//  vsb_attn_small_bf16  : tiny-head attention of the SAM two-way transformer (head_dim 16 / 32, 6 tokens
+//                         <-> 2304 image tokens); CUDA-core kernel, fp32 math.
+//                         (/root/reference/VisualSearch/model/segment_anything/modeling/transformer.py:220-242)
+#include "common.cuh"
+#include "vstar_b200.h"
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct AttnParams {
+  const bf16* q; const bf16* k; const bf16* v; bf16* o;
+  long long q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs;   // batch / row strides in elements; head h at +h*D
+  int B, H, Sq, Sk;
+  int causal;      // query i attends keys j <= i + (Sk - Sq)
+  float scale_log2;
+};
+
+constexpr int FA_BM = 64, FA_BN = 64;
+
+// swizzled element offset of (row, 16B-chunk) in a [rows][D] bf16 tile
+template <int D>
+__device__ __forceinline__ int swz(int row, int chunk) { return row * D + ((chunk ^ (row & 7)) << 3); }
+
+template <int D>
+__device__ __forceinline__ void load_tile(bf16* s, const bf16* g, long long rs, int row0, int nrows_valid, int tid) {
+  constexpr int CH = D / 8;
+  for (int i = tid; i < FA_BN * CH; i += 128) {
+    const int r = i / CH, c = i - r * CH;
+    const bool ok = (row0 + r) < nrows_valid;
+    const int rr = ok ? (row0 + r) : 0;
+    cp_async16(s + swz<D>(r, c), g + (long long)rr * rs + c * 8, ok);
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) flash_attn_kernel(const AttnParams p) {
+  extern __shared__ __align__(128) uint8_t fa_smem[];
+  bf16* sQ = reinterpret_cast<bf16*>(fa_smem);
+  bf16* sK = sQ + FA_BM * D;            // [2][64][D]
+  bf16* sV = sK + 2 * FA_BN * D;        // [2][64][D]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int m_blk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = m_blk * FA_BM;
+  const bf16* qg = p.q + (long long)b * p.q_bs + (long long)h * D;
+  const bf16* kg = p.k + (long long)b * p.k_bs + (long long)h * D;
+  const bf16* vg = p.v + (long long)b * p.v_bs + (long long)h * D;
+  const int off = p.Sk - p.Sq;
+
+  int n_blocks = (p.Sk + FA_BN - 1) / FA_BN;
+  if (p.causal) {
+    int last_key = q0 + FA_BM - 1 + off;            // largest key any query of this tile may see
+    if (last_key > p.Sk - 1) last_key = p.Sk - 1;
+    if (last_key < 0) last_key = 0;
+    const int nb = last_key / FA_BN + 1;
+    if (nb < n_blocks) n_blocks = nb;
+  }
+
+  load_tile<D>(sQ, qg, p.q_rs, q0, p.Sq, tid);
+  load_tile<D>(sK, kg, p.k_rs, 0, p.Sk, tid);
+  load_tile<D>(sV, vg, p.v_rs, 0, p.Sk, tid);
+  cp_async_commit();
+
+  uint32_t qf[D / 16][4];
+  float o_acc[D / 8][4];
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f; }
+  float row_max[2] = {-INFINITY, -INFINITY};
+  float row_sum[2] = {0.f, 0.f};
+
+  for (int nb = 0; nb < n_blocks; ++nb) {
+    const int buf = nb & 1;
+    cp_async_wait<0>();
+    __syncthreads();
+    if (nb + 1 < n_blocks) {
+      load_tile<D>(sK + (buf ^ 1) * FA_BN * D, kg, p.k_rs, (nb + 1) * FA_BN, p.Sk, tid);
+      load_tile<D>(sV + (buf ^ 1) * FA_BN * D, vg, p.v_rs, (nb + 1) * FA_BN, p.Sk, tid);
+      cp_async_commit();
+    }
+    if (nb == 0) {
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk)
+        ldmatrix_x4(qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], smem_u32(sQ + swz<D>(warp * 16 + (lane & 15), kk * 2 + (lane >> 4))));
+    }
+    const bf16* cK = sK + buf * FA_BN * D;
+    const bf16* cV = sV + buf * FA_BN * D;
+
+    // ---- S = Q K^T : 16 x 64 per warp
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t r0, r1, r2, r3;
+        ldmatrix_x4(r0, r1, r2, r3, smem_u32(cK + swz<D>(np * 16 + (lane & 7) + ((lane >> 4) << 3), kk * 2 + ((lane >> 3) & 1))));
+        mma_bf16_16816(s[2 * np], qf[kk], r0, r1);
+        mma_bf16_16816(s[2 * np + 1], qf[kk], r2, r3);
+      }
+    }
+    // ---- scale, mask, online softmax (rows g and g+8 of this warp's 16)
+    const int key0 = nb * FA_BN;
+    const int qrow0 = q0 + warp * 16 + g;
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = key0 + i * 8 + 2 * t + (e & 1);
+        const int qr = qrow0 + ((e >> 1) << 3);
+        float x = s[i][e] * p.scale_log2;
+        const bool masked = (key >= p.Sk) || (p.causal && key > qr + off);
+        x = masked ? -INFINITY : x;
+        s[i][e] = x;
+        mx[e >> 1] = fmaxf(mx[e >> 1], x);
+      }
+    }
+    float corr[2], mnew[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float m = mx[r];
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      mnew[r] = fmaxf(row_max[r], m);
+      const float msafe = (mnew[r] == -INFINITY) ? 0.f : mnew[r];
+      corr[r] = exp2f(row_max[r] - msafe);     // row_max = -inf -> 0
+      row_max[r] = mnew[r];
+      mnew[r] = msafe;
+    }
+    float psum[2] = {0.f, 0.f};
+    uint32_t pf[4][4];   // P as A-fragments for 4 k16 steps over the 64 keys
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float p0 = exp2f(s[i][0] - mnew[0]);
+      const float p1 = exp2f(s[i][1] - mnew[0]);
+      const float p2 = exp2f(s[i][2] - mnew[1]);
+      const float p3 = exp2f(s[i][3] - mnew[1]);
+      // the reference casts softmax output to bf16 before P@V; sum the *rounded* values so P rows sum to the normaliser
+      const uint32_t lo = pack_bf16x2(p0, p1);
+      const uint32_t hi = pack_bf16x2(p2, p3);
+      float2 a = unpack_bf16x2(lo), c = unpack_bf16x2(hi);
+      psum[0] += p0 + p1;
+      psum[1] += p2 + p3;
+      (void)a; (void)c;
+      pf[i >> 1][(i & 1) * 2 + 0] = lo;
+      pf[i >> 1][(i & 1) * 2 + 1] = hi;
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) row_sum[r] = row_sum[r] * corr[r] + psum[r];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) {
+      o_acc[i][0] *= corr[0]; o_acc[i][1] *= corr[0];
+      o_acc[i][2] *= corr[1]; o_acc[i][3] *= corr[1];
+    }
+    // ---- O += P V
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int dp = 0; dp < D / 16; ++dp) {
+        uint32_t r0, r1, r2, r3;
+        ldmatrix_x4_trans(r0, r1, r2, r3, smem_u32(cV + swz<D>(ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), dp * 2 + (lane >> 4))));
+        mma_bf16_16816(o_acc[2 * dp], pf[ks], r0, r1);
+        mma_bf16_16816(o_acc[2 * dp + 1], pf[ks], r2, r3);
+      }
+    }
+  }
+
+  // ---- finalize: O /= row_sum, stage through smem (reuse sQ), coalesced 16 B stores
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float sum = row_sum[r];
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    row_sum[r] = (sum > 0.f) ? 1.f / sum : 0.f;
+  }
+  __syncthreads();   // everyone is done reading sQ fragments / K / V
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) {
+    const int r_lo = warp * 16 + g, r_hi = r_lo + 8;
+    *reinterpret_cast<uint32_t*>(sQ + swz<D>(r_lo, i) + 2 * t) = pack_bf16x2(o_acc[i][0] * row_sum[0], o_acc[i][1] * row_sum[0]);
+    *reinterpret_cast<uint32_t*>(sQ + swz<D>(r_hi, i) + 2 * t) = pack_bf16x2(o_acc[i][2] * row_sum[1], o_acc[i][3] * row_sum[1]);
+  }
+  __syncthreads();
+  bf16* og = p.o + (long long)b * p.o_bs + (long long)h * D;
+  constexpr int CH = D / 8;
+  for (int i = tid; i < FA_BM * CH; i += 128) {
+    const int r = i / CH, c = i - r * CH;
+    if (q0 + r < p.Sq) *reinterpret_cast<uint4*>(og + (long long)(q0 + r) * p.o_rs + c * 8) = *reinterpret_cast<const uint4*>(sQ + swz<D>(r, c));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small attention (SAM two-way transformer): one warp per (batch, head, query); keys strided over lanes.
+// q [B, Nq, H*D], k/v [B, Nk, H*D] contiguous rows (row stride = ld*), D in {16, 32}.
+template <int D>
+__global__ void __launch_bounds__(128) attn_small_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ k,
+                                                         long long ldk, const bf16* __restrict__ v, long long ldv,
+                                                         bf16* __restrict__ o, long long ldo, int B, int H, int Nq, int Nk,
+                                                         float scale) {
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)B * H * Nq;
+  if (wid >= total) return;
+  const int qi = wid % Nq;
+  const int h = (wid / Nq) % H;
+  const int b = wid / ((long long)Nq * H);
+  const bf16* qp = q + ((long long)b * Nq + qi) * ldq + h * D;
+  float qv[D];
+#pragma unroll
+  for (int d = 0; d < D; d += 2) {
+    float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(qp + d));
+    qv[d] = f.x * scale; qv[d + 1] = f.y * scale;
+  }
+  float m = -INFINITY, l = 0.f;
+  float acc[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) acc[d] = 0.f;
+  for (int j = lane; j < Nk; j += 32) {
+    const bf16* kp = k + ((long long)b * Nk + j) * ldk + h * D;
+    const bf16* vp = v + ((long long)b * Nk + j) * ldv + h * D;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; d += 8) {
+      uint4 u = *reinterpret_cast<const uint4*>(kp + d);
+      float2 f;
+      f = unpack_bf16x2(u.x); s += qv[d] * f.x + qv[d + 1] * f.y;
+      f = unpack_bf16x2(u.y); s += qv[d + 2] * f.x + qv[d + 3] * f.y;
+      f = unpack_bf16x2(u.z); s += qv[d + 4] * f.x + qv[d + 5] * f.y;
+      f = unpack_bf16x2(u.w); s += qv[d + 6] * f.x + qv[d + 7] * f.y;
+    }
+    const float mn = fmaxf(m, s);
+    const float c = __expf(m - mn);
+    const float pj = __expf(s - mn);
+    l = l * c + pj;
+#pragma unroll
+    for (int d = 0; d < D; d += 8) {
+      uint4 u = *reinterpret_cast<const uint4*>(vp + d);
+      float2 f;
+      f = unpack_bf16x2(u.x); acc[d] = acc[d] * c + pj * f.x; acc[d + 1] = acc[d + 1] * c + pj * f.y;
+      f = unpack_bf16x2(u.y); acc[d + 2] = acc[d + 2] * c + pj * f.x; acc[d + 3] = acc[d + 3] * c + pj * f.y;
+      f = unpack_bf16x2(u.z); acc[d + 4] = acc[d + 4] * c + pj * f.x; acc[d + 5] = acc[d + 5] * c + pj * f.y;
+      f = unpack_bf16x2(u.w); acc[d + 6] = acc[d + 6] * c + pj * f.x; acc[d + 7] = acc[d + 7] * c + pj * f.y;
+    }
+    m = mn;
+  }
+  // merge the 32 per-lane partial softmaxes
+  float mg = warp_max(m);
+  const float c = (m == -INFINITY) ? 0.f : __expf(m - mg);
+  l = warp_sum(l * c);
+  const float inv = 1.f / l;
+  bf16* op = o + ((long long)b * Nq + qi) * ldo + h * D;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const float a = warp_sum(acc[d] * c);
+    if (lane == (d & 31)) op[d] = f2bf(a * inv);
+  }
+}
+
+}  // namespace
+
+extern "C" int vsb_flash_attn_bf16(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_rs,
+                                   long long k_bs, long long k_rs, long long v_bs, long long v_rs, long long o_bs,
+                                   long long o_rs, int B, int H, int Sq, int Sk, int D, int causal, float scale, void* stream) {
+  VSB_CHECK_ARG(q && k && v && o, "vsb_flash_attn_bf16: null pointer");
+  VSB_CHECK_ARG(D == 64 || D == 128, "vsb_flash_attn_bf16: head_dim %d unsupported (64/128)", D);
+  VSB_CHECK_ARG(B > 0 && H > 0 && Sq > 0 && Sk > 0, "vsb_flash_attn_bf16: bad shape");
+  VSB_CHECK_ARG(q_rs % 8 == 0 && k_rs % 8 == 0 && v_rs % 8 == 0 && o_rs % 8 == 0 && q_bs % 8 == 0 && k_bs % 8 == 0 &&
+                    v_bs % 8 == 0 && o_bs % 8 == 0,
+                "vsb_flash_attn_bf16: strides must be multiples of 8 elements (16 B)");
+  VSB_CHECK_ARG(((uintptr_t)q & 15) == 0 && ((uintptr_t)k & 15) == 0 && ((uintptr_t)v & 15) == 0 && ((uintptr_t)o & 15) == 0,
+                "vsb_flash_attn_bf16: pointers must be 16-byte aligned");
+  AttnParams p;
+  p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v; p.o = (bf16*)o;
+  p.q_bs = q_bs; p.q_rs = q_rs; p.k_bs = k_bs; p.k_rs = k_rs; p.v_bs = v_bs; p.v_rs = v_rs; p.o_bs = o_bs; p.o_rs = o_rs;
+  p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk; p.causal = causal;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid((Sq + FA_BM - 1) / FA_BM, H, B);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (D == 64) {
+    const int smem = (FA_BM + 4 * FA_BN) * 64 * 2;
+    static bool set64 = false;
+    if (!set64) { VSB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set64 = true; }
+    flash_attn_kernel<64><<<grid, 128, smem, st>>>(p);
+  } else {
+    const int smem = (FA_BM + 4 * FA_BN) * 128 * 2;
+    static bool set128 = false;
+    if (!set128) { VSB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set128 = true; }
+    flash_attn_kernel<128><<<grid, 128, smem, st>>>(p);
+  }
+  VSB_LAUNCH_CHECK();
+  return VSB_OK;
+}
+
+extern "C" int vsb_attn_small_bf16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o,
+                                   long long ldo, int B, int H, int Nq, int Nk, int D, float scale, void* stream) {
+  VSB_CHECK_ARG(q && k && v && o, "vsb_attn_small_bf16: null pointer");
+  VSB_CHECK_ARG(D == 16 || D == 32, "vsb_attn_small_bf16: head_dim %d unsupported (16/32)", D);
+  VSB_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0, "vsb_attn_small_bf16: ld must be multiples of 8");
+  const long long warps = (long long)B * H * Nq;
+  if (warps <= 0) return VSB_OK;
+  const int blocks = (int)((warps + 3) / 4);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (D == 16)
+    attn_small_kernel<16><<<blocks, 128, 0, st>>>((const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (bf16*)o, ldo, B, H, Nq, Nk, scale);
+  else
+    attn_small_kernel<32><<<blocks, 128, 0, st>>>((const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (bf16*)o, ldo, B, H, Nq, Nk, scale);
+  VSB_LAUNCH_CHECK();
+  return VSB_OK;
+}

@@ -1,0 +1,548 @@
+// vsb_gemm_bf16: C[M,N] = epilogue(A[M,K] . W[N,K]^T + bias) (+ residual)
+//
+// Hand-written sm_100a GEMM: TMA (cp.async.bulk.tensor, 128B swizzle) -> shared
+// memory ring -> tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM) ->
+// tcgen05.ld epilogue (bias / activation / SwiGLU / residual / row remap) ->
+// global.  Persistent: one CTA per SM loops over 128 x BN output tiles; the
+// TMEM accumulator is double buffered so the epilogue of tile i overlaps the
+// MMAs of tile i+1.
+//
+// This one kernel carries every nn.Linear on the hot path (reference op sites
+// H1-H3, H5, H6, H8-H10, H12-H15 of SURVEY.md §2b): CLIP/OWL patch-embed
+// (as im2col GEMM), all ViT and Llama projections, the LLaVA mm_projector,
+// lm_head, the [LOC]-row MLPs, OWL class/box heads and the SAM decoder linears
+// and 3x3 convs (im2col).
+//
+// Warp roles (256 threads): warp 0 = TMA producer (1 lane), warp 1 = MMA issuer
+// (1 lane), warp 2 = TMEM alloc/dealloc, warp 3 idle, warps 4-7 = epilogue
+// (warp w owns TMEM lanes 32*(w%4) .. +31 == output rows of the tile).
+#include "common.cuh"
+#include "vstar_b200.h"
+
+#include <mutex>
+#include <unordered_map>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;   // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int UMMA_K = 16;
+
+struct GemmParams {
+  void* C;
+  const bf16* bias;
+  const void* residual;
+  long long ldc, ldr;
+  int M, N, K;
+  int epilogue;        // VSB_EPI_*
+  int out_fp32;        // C (and residual) element type: 0 bf16, 1 fp32
+  int rows_per_group;  // output row remap: r = (m / rpg) * group_stride + group_offset + m % rpg
+  long long group_stride, group_offset;
+  int tiles_m, tiles_n;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread retire
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread i <- lane (base+i), v[j] <- column (base+j)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled shared-memory operand descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows * 128 B = 1024)
+//   [46,48) version=1 (sm_100) | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor for kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1),
+// K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+};
+
+__device__ __forceinline__ float apply_act(float x, int epi) {
+  switch (epi) {
+    case VSB_EPI_QUICK_GELU: return quick_gelu_f(x);
+    case VSB_EPI_GELU: return gelu_erf_f(x);
+    case VSB_EPI_RELU: return fmaxf(x, 0.f);
+    default: return x;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using L = SmemLayout<BN>;
+  constexpr int STAGES = L::STAGES;
+  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // double-buffered accumulator (power of 2: 128/256/512)
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);   // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % p.tiles_m;
+        const int n_blk = tile / p.tiles_m;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, kb * BK, m_blk * BM, &full_bar[stage]);
+          tma_load_2d(sb, &tmB, kb * BK, n_blk * BN, &full_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+          const uint64_t da = make_smem_desc(sa);
+          const uint64_t db = make_smem_desc(sb);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in the (addr>>4) field
+            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);   // frees this smem stage once the MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);       // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                 // TMEM lane quarter
+    int it = 0;
+    const bool swiglu = (p.epilogue == VSB_EPI_SWIGLU);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile % p.tiles_m;
+      const int n_blk = tile / p.tiles_m;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int m = m_blk * BM + q * 32 + lane;
+      const bool row_ok = m < p.M;
+      long long orow = 0;
+      if (row_ok) orow = (long long)(m / p.rows_per_group) * p.group_stride + p.group_offset + (m % p.rows_per_group);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32);
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        const int n0 = n_blk * BN + c * 32;
+        if (!row_ok || n0 >= p.N) continue;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+          if (n0 + 32 <= p.N) {
+            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              uint4 b = __ldg(bp + j4);
+              float2 t;
+              t = unpack_bf16x2(b.x); f[j4 * 8 + 0] += t.x; f[j4 * 8 + 1] += t.y;
+              t = unpack_bf16x2(b.y); f[j4 * 8 + 2] += t.x; f[j4 * 8 + 3] += t.y;
+              t = unpack_bf16x2(b.z); f[j4 * 8 + 4] += t.x; f[j4 * 8 + 5] += t.y;
+              t = unpack_bf16x2(b.w); f[j4 * 8 + 6] += t.x; f[j4 * 8 + 7] += t.y;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) f[j] += bf2f(p.bias[n0 + j]);
+          }
+        }
+        if (swiglu) {
+          // interleaved weight rows: even column = gate_j, odd column = up_j -> out column (n0/2 + j)
+          const int on0 = n0 >> 1;
+          const int nout = p.N >> 1;
+          float o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = silu_f(f[2 * j]) * f[2 * j + 1];
+          bf16* crow = reinterpret_cast<bf16*>(p.C) + orow * p.ldc + on0;
+          if (on0 + 16 <= nout && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+            uint4 w0, w1;
+            w0.x = pack_bf16x2(o[0], o[1]); w0.y = pack_bf16x2(o[2], o[3]); w0.z = pack_bf16x2(o[4], o[5]); w0.w = pack_bf16x2(o[6], o[7]);
+            w1.x = pack_bf16x2(o[8], o[9]); w1.y = pack_bf16x2(o[10], o[11]); w1.z = pack_bf16x2(o[12], o[13]); w1.w = pack_bf16x2(o[14], o[15]);
+            reinterpret_cast<uint4*>(crow)[0] = w0;
+            reinterpret_cast<uint4*>(crow)[1] = w1;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (on0 + j < nout) crow[j] = f2bf(o[j]);
+          }
+          continue;
+        }
+        if (p.epilogue != VSB_EPI_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.epilogue);
+        }
+        const bool full = (n0 + 32 <= p.N);
+        if (p.out_fp32) {
+          float* crow = reinterpret_cast<float*>(p.C) + orow * p.ldc + n0;
+          const float* rrow = p.residual ? reinterpret_cast<const float*>(p.residual) + orow * p.ldr + n0 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (full || n0 + j < p.N) {
+              float x = f[j];
+              if (rrow) x += rrow[j];
+              crow[j] = x;
+            }
+          }
+        } else {
+          bf16* crow = reinterpret_cast<bf16*>(p.C) + orow * p.ldc + n0;
+          const bf16* rrow = p.residual ? reinterpret_cast<const bf16*>(p.residual) + orow * p.ldr + n0 : nullptr;
+          const bool vec_ok = full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) &&
+                              (rrow == nullptr || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
+          if (vec_ok) {
+            if (rrow) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                uint4 r = reinterpret_cast<const uint4*>(rrow)[j4];
+                float2 t;
+                t = unpack_bf16x2(r.x); f[j4 * 8 + 0] += t.x; f[j4 * 8 + 1] += t.y;
+                t = unpack_bf16x2(r.y); f[j4 * 8 + 2] += t.x; f[j4 * 8 + 3] += t.y;
+                t = unpack_bf16x2(r.z); f[j4 * 8 + 4] += t.x; f[j4 * 8 + 5] += t.y;
+                t = unpack_bf16x2(r.w); f[j4 * 8 + 6] += t.x; f[j4 * 8 + 7] += t.y;
+              }
+            }
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              uint4 w;
+              w.x = pack_bf16x2(f[j4 * 8 + 0], f[j4 * 8 + 1]);
+              w.y = pack_bf16x2(f[j4 * 8 + 2], f[j4 * 8 + 3]);
+              w.z = pack_bf16x2(f[j4 * 8 + 4], f[j4 * 8 + 5]);
+              w.w = pack_bf16x2(f[j4 * 8 + 6], f[j4 * 8 + 7]);
+              reinterpret_cast<uint4*>(crow)[j4] = w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (full || n0 + j < p.N) {
+                float x = f[j];
+                if (rrow) x += bf2f(rrow[j]);
+                crow[j] = f2bf(x);
+              }
+            }
+          }
+        }
+      }
+      // release this accumulator buffer to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  long long rows, cols, ld;
+  int box_rows;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    h ^= std::hash<long long>()(k.rows * 1315423911LL + k.cols) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+    h ^= std::hash<long long>()(k.ld * 31 + k.box_rows) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+
+// 2D bf16 row-major [rows, cols] with leading dimension ld (elements); box = {64 cols, box_rows}
+int make_tensor_map(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  MapKey key{ptr, rows, cols, ld, box_rows};
+  {
+    std::lock_guard<std::mutex> g(g_map_mu);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) {
+      *out = it->second;
+      return VSB_OK;
+    }
+  }
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    vsb_set_error("cuTensorMapEncodeTiled entry point not available");
+    return VSB_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    vsb_set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%lld cols=%lld ld=%lld box_rows=%d", (int)r, ptr, rows,
+                  cols, ld, box_rows);
+    return VSB_ERR_CUDA;
+  }
+  {
+    std::lock_guard<std::mutex> g(g_map_mu);
+    if (g_map_cache.size() > 8192) g_map_cache.clear();
+    g_map_cache[key] = *out;
+  }
+  return VSB_OK;
+}
+
+template <int BN>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int max_ctas, cudaStream_t stream) {
+  using L = SmemLayout<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VSB_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  p.tiles_m = (p.M + BM - 1) / BM;
+  p.tiles_n = (p.N + BN - 1) / BN;
+  int tiles = p.tiles_m * p.tiles_n;
+  int grid = tiles < max_ctas ? tiles : max_ctas;
+  gemm_bf16_tcgen05_kernel<BN><<<grid, 256, L::TOTAL, stream>>>(tmA, tmB, p);
+  VSB_LAUNCH_CHECK();
+  return VSB_OK;
+}
+
+int g_force_bn = 0;
+int g_max_ctas = 0;
+
+}  // namespace
+
+extern "C" int vsb_gemm_set_tuning(int force_bn, int max_ctas) {
+  g_force_bn = force_bn;
+  g_max_ctas = max_ctas;
+  return VSB_OK;
+}
+
+extern "C" int vsb_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M,
+                             int N, int K, const void* bias, const void* residual, long long ldr, int epilogue,
+                             int out_fp32, int rows_per_group, long long group_stride, long long group_offset,
+                             void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VSB_CHECK_ARG(A && W && C, "vsb_gemm_bf16: null pointer");
+  VSB_CHECK_ARG(M > 0 && N > 0 && K > 0, "vsb_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
+  VSB_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0, "vsb_gemm_bf16: lda/ldw must be multiples of 8 (TMA 16 B stride), got %lld %lld", lda, ldw);
+  VSB_CHECK_ARG(lda >= K && ldw >= K, "vsb_gemm_bf16: leading dimension smaller than K");
+  VSB_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+                "vsb_gemm_bf16: A/W must be 16-byte aligned");
+  VSB_CHECK_ARG(epilogue >= VSB_EPI_NONE && epilogue <= VSB_EPI_SWIGLU, "vsb_gemm_bf16: bad epilogue %d", epilogue);
+  VSB_CHECK_ARG(!(epilogue == VSB_EPI_SWIGLU && (out_fp32 || residual || (N & 1))), "vsb_gemm_bf16: SwiGLU epilogue is bf16, no residual, even N");
+  if (rows_per_group <= 0) {
+    rows_per_group = M;
+    group_stride = 0;
+    group_offset = 0;
+  }
+  GemmParams p;
+  p.C = C;
+  p.bias = reinterpret_cast<const bf16*>(bias);
+  p.residual = residual;
+  p.ldc = ldc;
+  p.ldr = ldr;
+  p.M = M; p.N = N; p.K = K;
+  p.epilogue = epilogue;
+  p.out_fp32 = out_fp32;
+  p.rows_per_group = rows_per_group;
+  p.group_stride = group_stride;
+  p.group_offset = group_offset;
+
+  const int sms = g_max_ctas > 0 ? g_max_ctas : vsb_num_sms();
+  // tile-width choice: minimise (waves * BN) ~ time; prefer the wider tile on ties (less A re-streaming)
+  int bn = 64;
+  if (g_force_bn) {
+    bn = g_force_bn;
+  } else if (N > 64) {
+    const int tm = (M + BM - 1) / BM;
+    long long best = -1;
+    const int cands[3] = {256, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+      int c = cands[i];
+      if (c == 64 && N > 512) continue;
+      long long tiles = (long long)tm * ((N + c - 1) / c);
+      long long waves = (tiles + sms - 1) / sms;
+      long long cost = waves * c;
+      if (best < 0 || cost < best) { best = cost; bn = c; }
+    }
+  }
+  CUtensorMap tmA, tmB;
+  int r = make_tensor_map(&tmA, A, M, K, lda, BM);
+  if (r) return r;
+  r = make_tensor_map(&tmB, W, N, K, ldw, bn);
+  if (r) return r;
+  if (bn == 256) return launch_gemm<256>(tmA, tmB, p, sms, stream);
+  if (bn == 128) return launch_gemm<128>(tmA, tmB, p, sms, stream);
+  return launch_gemm<64>(tmA, tmB, p, sms, stream);
+}

@@ -1,0 +1,308 @@
+// Post-backbone kernels of the VSM hot path: OWL-ViT class/box head epilogues, SAM mask-decoder
+// upscaling helpers (bilinear x2, 3x3 im2col, hyper-network dot), the full-resolution target-cue
+// heatmap (bilinear + clamp) with its reductions, and the quad-tree rectangle sums used by the search
+// controller.  All HBM/L2-bound streaming kernels (coalesced, vectorised where rows are contiguous).
+#include "common.cuh"
+#include "vstar_b200.h"
+
+namespace {
+
+// ---------------------------------------------------------------- OWL class head epilogue
+// y [R, ldy] fp32 = [dense0(x) (Q cols) | logit_shift | logit_scale]  (one GEMM with stacked weights)
+// logit = (<y/(|y|+1e-6), q/(|q|+1e-6)> + shift) * (elu(scale) + 1)
+//   (transformers/models/owlvit/modeling_owlvit.py:1043-1062); one warp per row.
+__global__ void __launch_bounds__(128) owl_class_post_kernel(const float* __restrict__ y, long long ldy,
+                                                             const bf16* __restrict__ query, long long ldq, int rows_per_crop,
+                                                             long long R, int Q, float* __restrict__ logits,
+                                                             float* __restrict__ scores) {
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const int b = row / rows_per_crop;
+  const float* yr = y + row * ldy;
+  const bf16* qr = query + (long long)b * ldq;
+  float yy = 0.f, qq = 0.f, yq = 0.f;
+  for (int i = lane; i < Q; i += 32) {
+    const float a = yr[i], c = bf2f(qr[i]);
+    yy += a * a; qq += c * c; yq += a * c;
+  }
+  yy = warp_sum(yy); qq = warp_sum(qq); yq = warp_sum(yq);
+  if (lane == 0) {
+    const float dot = yq / ((sqrtf(yy) + 1e-6f) * (sqrtf(qq) + 1e-6f));
+    const float shift = yr[Q], sc = yr[Q + 1];
+    const float scale = (sc > 0.f ? sc : expm1f(sc)) + 1.f;
+    const float l = (dot + shift) * scale;
+    logits[row] = l;
+    if (scores) scores[row] = 1.f / (1.f + expf(-l));
+  }
+}
+
+// boxes = sigmoid(y[:, :4] + box_bias[row % rows_per_crop])   (owlvit.py:79-100)
+__global__ void owl_box_post_kernel(const float* __restrict__ y, long long ldy, const float* __restrict__ bias, int rows_per_crop,
+                                    long long R, float* __restrict__ boxes) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= R * 4) return;
+  const long long row = i >> 2;
+  const int c = i & 3;
+  const float v = y[row * ldy + c] + bias[(row % rows_per_crop) * 4 + c];
+  boxes[i] = 1.f / (1.f + expf(-v));
+}
+
+// ---------------------------------------------------------------- bilinear x2, NHWC bf16 (fp32 math, bf16 out)
+// torch.nn.functional.interpolate(x.float(), scale_factor=2, mode="bilinear").to(bf16)
+//   (/root/reference/VisualSearch/model/segment_anything/modeling/mask_decoder.py:24-27)
+__global__ void upsample2x_nhwc_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int H, int W, int C) {
+  const int OH = 2 * H, OW = 2 * W;
+  const long long pix = blockIdx.x;             // b*OH*OW + oy*OW + ox
+  const int ox = pix % OW;
+  const int oy = (pix / OW) % OH;
+  const int b = pix / ((long long)OW * OH);
+  float sy = 0.5f * (oy + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
+  float sx = 0.5f * (ox + 0.5f) - 0.5f; if (sx < 0.f) sx = 0.f;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+  const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
+  const bf16* p00 = x + (((long long)b * H + y0) * W + x0) * C;
+  const bf16* p01 = x + (((long long)b * H + y0) * W + x1) * C;
+  const bf16* p10 = x + (((long long)b * H + y1) * W + x0) * C;
+  const bf16* p11 = x + (((long long)b * H + y1) * W + x1) * C;
+  bf16* o = y + pix * C;
+  for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {
+    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p00 + c));
+    const float2 bb = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p01 + c));
+    const float2 cc = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p10 + c));
+    const float2 d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p11 + c));
+    const float r0 = hy * (hx * a.x + lx * bb.x) + ly * (hx * cc.x + lx * d.x);
+    const float r1 = hy * (hx * a.y + lx * bb.y) + ly * (hx * cc.y + lx * d.y);
+    *reinterpret_cast<uint32_t*>(o + c) = pack_bf16x2(r0, r1);
+  }
+}
+
+// ---------------------------------------------------------------- im2col for 3x3 / pad 1 / stride 1, NHWC bf16
+// A[(b,y,x), (ky*3+kx)*C + c] = X[b, y+ky-1, x+kx-1, c] (0 outside); conv weight must be permuted to [Cout, ky, kx, Cin].
+__global__ void im2col3x3_nhwc_kernel(const bf16* __restrict__ x, bf16* __restrict__ A, int B, int H, int W, int C) {
+  const long long pix = blockIdx.x;
+  const int ox = pix % W;
+  const int oy = (pix / W) % H;
+  const int b = pix / ((long long)W * H);
+  const int c8 = C >> 3;
+  uint4* dst = reinterpret_cast<uint4*>(A + pix * 9 * C);
+  for (int i = threadIdx.x; i < 9 * c8; i += blockDim.x) {
+    const int tap = i / c8, cc = i - tap * c8;
+    const int iy = oy + tap / 3 - 1, ix = ox + tap % 3 - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = *(reinterpret_cast<const uint4*>(x + (((long long)b * H + iy) * W + ix) * C) + cc);
+    dst[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------- masks[b,p] = sum_c hyper[b,c] * up[b,p,c]
+//   (mask_decoder.py:178-181, mask token 0 only since multimask_output=False)
+__global__ void mask_dot_kernel(const bf16* __restrict__ up, const bf16* __restrict__ hyper, float* __restrict__ out, int B,
+                                long long P, int C) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)B * P) return;
+  const int b = i / P;
+  const bf16* u = up + i * C;
+  const bf16* hrow = hyper + (long long)b * C;
+  float s = 0.f;
+  for (int c = 0; c < C; c += 8) {
+    uint4 a = *reinterpret_cast<const uint4*>(u + c);
+    uint4 hh = __ldg(reinterpret_cast<const uint4*>(hrow + c));
+    float2 p, q;
+    p = unpack_bf16x2(a.x); q = unpack_bf16x2(hh.x); s += p.x * q.x + p.y * q.y;
+    p = unpack_bf16x2(a.y); q = unpack_bf16x2(hh.y); s += p.x * q.x + p.y * q.y;
+    p = unpack_bf16x2(a.z); q = unpack_bf16x2(hh.z); s += p.x * q.x + p.y * q.y;
+    p = unpack_bf16x2(a.w); q = unpack_bf16x2(hh.w); s += p.x * q.x + p.y * q.y;
+  }
+  out[i] = s;
+}
+
+// ---------------------------------------------------------------- target-cue heatmap
+// F.interpolate(low_res.float(), (h, w), mode="bilinear", align_corners=False) then clamp(min=0)
+//   (/root/reference/VisualSearch/model/VSM.py:534-537; /root/reference/visual_search.py:223-224)
+// Same arithmetic order as ATen's upsample_bilinear2d (fp32 accscalar).  Also emits per-block partial
+// (max, min, sum) so the search controller never has to re-read the H x W map for its statistics.
+__global__ void __launch_bounds__(256) heatmap_kernel(const float* __restrict__ low, int LH, int LW, float* __restrict__ out, int h,
+                                                      int w, int do_clamp, float* __restrict__ partial) {
+  __shared__ float smax[8], smin[8], ssum[8];
+  const float rh = (float)LH / (float)h, rw = (float)LW / (float)w;
+  const long long n = (long long)h * w;
+  float mx = -INFINITY, mn = INFINITY, sm = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int oy = i / w, ox = i - (long long)oy * w;
+    float sy = rh * (oy + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
+    float sx = rw * (ox + 0.5f) - 0.5f; if (sx < 0.f) sx = 0.f;
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < LH - 1 ? 1 : 0), x1 = x0 + (x0 < LW - 1 ? 1 : 0);
+    const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    float v = hy * (hx * low[y0 * LW + x0] + lx * low[y0 * LW + x1]) + ly * (hx * low[y1 * LW + x0] + lx * low[y1 * LW + x1]);
+    if (do_clamp) v = fmaxf(v, 0.f);
+    out[i] = v;
+    mx = fmaxf(mx, v); mn = fminf(mn, v); sm += v;
+  }
+  mx = warp_max(mx); mn = warp_min(mn); sm = warp_sum(sm);
+  const int wid = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { smax[wid] = mx; smin[wid] = mn; ssum[wid] = sm; }
+  __syncthreads();
+  if (threadIdx.x == 0 && partial) {
+    for (int k = 1; k < 8; ++k) { mx = fmaxf(mx, smax[k]); mn = fminf(mn, smin[k]); sm += ssum[k]; }
+    partial[blockIdx.x * 3 + 0] = mx; partial[blockIdx.x * 3 + 1] = mn; partial[blockIdx.x * 3 + 2] = sm;
+  }
+}
+
+__global__ void __launch_bounds__(256) stats_final_kernel(const float* __restrict__ partial, int n, float* __restrict__ out3) {
+  __shared__ float smax[8], smin[8];
+  __shared__ double ssum[8];
+  float mx = -INFINITY, mn = INFINITY;
+  double sm = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    mx = fmaxf(mx, partial[i * 3]); mn = fminf(mn, partial[i * 3 + 1]); sm += (double)partial[i * 3 + 2];
+  }
+  mx = warp_max(mx); mn = warp_min(mn);
+  for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+  const int wid = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { smax[wid] = mx; smin[wid] = mn; ssum[wid] = sm; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) { mx = fmaxf(mx, smax[k]); mn = fminf(mn, smin[k]); sm += ssum[k]; }
+    out3[0] = mx; out3[1] = mn; out3[2] = (float)sm;
+  }
+}
+
+// ---------------------------------------------------------------- rectangle sums of the normalised heatmap
+// out[r] = sum over rect r of  (hm[y,x] - sub) * mul     (normalize_score folded in: sub = min, mul = 1/(max-min), or 0/0)
+//   (/root/reference/visual_search.py:255-275).  One block per rectangle, fp32 per-thread partials, fp64 block combine.
+__global__ void __launch_bounds__(256) rect_sums_kernel(const float* __restrict__ hm, int h, int w, const int* __restrict__ rects,
+                                                        int nrects, const float* __restrict__ stats, double* __restrict__ out) {
+  __shared__ double red[8];
+  const int r = blockIdx.x;
+  if (r >= nrects) return;
+  int x0 = rects[r * 4 + 0], y0 = rects[r * 4 + 1], rw = rects[r * 4 + 2], rh = rects[r * 4 + 3];
+  int x1 = x0 + rw, y1 = y0 + rh;
+  if (x0 < 0) x0 = 0; if (y0 < 0) y0 = 0; if (x1 > w) x1 = w; if (y1 > h) y1 = h;
+  const float mx = stats[0], mn = stats[1];
+  const float mul = (mx != mn) ? 1.f / (mx - mn) : 0.f;
+  const float sub = (mx != mn) ? mn : 0.f;
+  const long long cnt = (x1 > x0 && y1 > y0) ? (long long)(x1 - x0) * (y1 - y0) : 0;
+  const int cw = x1 - x0;
+  float acc = 0.f;
+  double dacc = 0.0;
+  int k = 0;
+  for (long long i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int yy = y0 + i / cw, xx = x0 + i % cw;
+    acc += (hm[(long long)yy * w + xx] - sub) * mul;
+    if (++k == 256) { dacc += acc; acc = 0.f; k = 0; }
+  }
+  dacc += acc;
+  for (int o = 16; o > 0; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dacc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < 8; ++q) dacc += red[q];
+    out[r] = dacc;
+  }
+}
+
+// strided 2-D copy of 16-byte vectors: dst[r, :] = src[r, :]
+__global__ void copy2d_kernel(const uint4* __restrict__ src, long long lds16, uint4* __restrict__ dst, long long ldd16, long long rows,
+                              int cols16) {
+  const long long n = rows * cols16;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols16;
+    const int c = i - r * cols16;
+    dst[r * ldd16 + c] = src[r * lds16 + c];
+  }
+}
+
+}  // namespace
+
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int vsb_owl_class_post(const void* y, long long ldy, const void* query, long long ldq, int rows_per_crop, long long R, int Q,
+                                  void* logits, void* scores, void* stream) {
+  VSB_CHECK_ARG(y && query && logits && Q > 0 && rows_per_crop > 0, "vsb_owl_class_post: bad args");
+  if (R <= 0) return VSB_OK;
+  const int blocks = (int)((R + 3) / 4);
+  owl_class_post_kernel<<<blocks, 128, 0, STREAM(stream)>>>((const float*)y, ldy, (const bf16*)query, ldq, rows_per_crop, R, Q,
+                                                            (float*)logits, (float*)scores);
+  VSB_LAUNCH_CHECK();
+  return VSB_OK;
+}
+
+extern "C" int vsb_owl_box_post(const void* y, long long ldy, const void* box_bias, int rows_per_crop, long long R, void* boxes,
+                                void* stream) {
+  VSB_CHECK_ARG(y && box_bias && boxes && rows_per_crop > 0, "vsb_owl_box_post: bad args");
+  if (R <= 0) return VSB_OK;
+  const int blocks = (int)((R * 4 + 255) / 256);
+  owl_box_post_kernel<<<blocks, 256, 0, STREAM(stream)>>>((const float*)y, ldy, (const float*)box_bias, rows_per_crop, R, (float*)boxes);
+  VSB_LAUNCH_CHECK();
+  return VSB_OK;
+}
+
+extern "C" int vsb_upsample2x_nhwc_bf16(const void* x, void* y, int B, int H, int W, int C, void* stream) {
+  VSB_CHECK_ARG(x && y && C % 2 == 0, "vsb_upsample2x_nhwc_bf16: bad args");
+  const long long pix = (long long)B * 4 * H * W;
+  if (pix <= 0) return VSB_OK;
+  const int threads = C / 2 < 128 ? (C / 2 < 32 ? 32 : C / 2) : 128;
+  upsample2x_nhwc_kernel<<<(unsigned)pix, threads, 0, STREAM(stream)>>>((const bf16*)x, (bf16*)y, B, H, W, C);
+  VSB_LAUNCH_CHECK();
+  return VSB_OK;
+}
+
+extern "C" int vsb_im2col3x3_nhwc_bf16(const void* x, void* A, int B, int H, int W, int C, void* stream) {
+  VSB_CHECK_ARG(x && A && C % 8 == 0, "vsb_im2col3x3_nhwc_bf16: bad args");
+  const long long pix = (long long)B * H * W;
+  if (pix <= 0) return VSB_OK;
+  im2col3x3_nhwc_kernel<<<(unsigned)pix, 128, 0, STREAM(stream)>>>((const bf16*)x, (bf16*)A, B, H, W, C);
+  VSB_LAUNCH_CHECK();
+  return VSB_OK;
+}
+
+extern "C" int vsb_mask_dot_bf16(const void* up, const void* hyper, void* out, int B, long long P, int C, void* stream) {
+  VSB_CHECK_ARG(up && hyper && out && C % 8 == 0, "vsb_mask_dot_bf16: bad args");
+  const long long n = (long long)B * P;
+  if (n <= 0) return VSB_OK;
+  mask_dot_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM(stream)>>>((const bf16*)up, (const bf16*)hyper, (float*)out, B, P, C);
+  VSB_LAUNCH_CHECK();
+  return VSB_OK;
+}
+
+// out [h,w] fp32, stats3 = (max, min, sum) of the written map; scratch >= 3*VSB_HEATMAP_MAX_BLOCKS floats
+extern "C" int vsb_heatmap_bilinear_f32(const void* low, int LH, int LW, void* out, int h, int w, int do_clamp, void* scratch,
+                                        void* stats3, void* stream) {
+  VSB_CHECK_ARG(low && out && h > 0 && w > 0 && LH > 0 && LW > 0, "vsb_heatmap_bilinear_f32: bad args");
+  VSB_CHECK_ARG((scratch != nullptr) == (stats3 != nullptr), "vsb_heatmap_bilinear_f32: scratch and stats3 go together");
+  const long long n = (long long)h * w;
+  long long blocks = (n + 256 * 8 - 1) / (256 * 8);
+  if (blocks > VSB_HEATMAP_MAX_BLOCKS) blocks = VSB_HEATMAP_MAX_BLOCKS;
+  if (blocks < 1) blocks = 1;
+  heatmap_kernel<<<(unsigned)blocks, 256, 0, STREAM(stream)>>>((const float*)low, LH, LW, (float*)out, h, w, do_clamp, (float*)scratch);
+  VSB_LAUNCH_CHECK();
+  if (stats3) {
+    stats_final_kernel<<<1, 256, 0, STREAM(stream)>>>((const float*)scratch, (int)blocks, (float*)stats3);
+    VSB_LAUNCH_CHECK();
+  }
+  return VSB_OK;
+}
+
+extern "C" int vsb_rect_sums_f32(const void* hm, int h, int w, const void* rects, int nrects, const void* stats3, void* out_f64,
+                                 void* stream) {
+  VSB_CHECK_ARG(hm && rects && stats3 && out_f64, "vsb_rect_sums_f32: null pointer");
+  if (nrects <= 0) return VSB_OK;
+  rect_sums_kernel<<<nrects, 256, 0, STREAM(stream)>>>((const float*)hm, h, w, (const int*)rects, nrects, (const float*)stats3, (double*)out_f64);
+  VSB_LAUNCH_CHECK();
+  return VSB_OK;
+}
+
+extern "C" int vsb_copy2d_b16(const void* src, long long lds, void* dst, long long ldd, long long rows, int cols, void* stream) {
+  VSB_CHECK_ARG(src && dst && cols % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0, "vsb_copy2d_b16: cols/ld must be multiples of 8 elements");
+  VSB_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "vsb_copy2d_b16: 16-byte alignment required");
+  const long long n = rows * (cols / 8);
+  if (n <= 0) return VSB_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  copy2d_kernel<<<(unsigned)blocks, 256, 0, STREAM(stream)>>>((const uint4*)src, lds / 8, (uint4*)dst, ldd / 8, rows, cols / 8);
+  VSB_LAUNCH_CHECK();
+  return VSB_OK;
+}
