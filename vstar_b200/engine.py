@@ -281,10 +281,11 @@ class VSMEngine:
         assert T <= self.max_tokens
         ct, S = self.clip_tokens(images_clip)                       # [B*257, Cc]
         x = torch.empty((B * T, c.hidden), dtype=BF, device=self.dev)
-        # projector over all 257 rows would waste the CLS row; project the 256 patch rows of every crop with a strided view
-        ctv = ct.view(B, S, -1)[:, 1:, :]                           # [B,256,Cc] non-contiguous
-        for b in range(B):
-            ops.gemm(ctv[b], self.w.mm_w, out=x[b * T + img_pos: b * T + img_pos + n_img], bias=self.w.mm_b)
+        # mm_projector over all B*257 rows in ONE GEMM whose epilogue scatters each crop's rows straight into the LLM
+        # input buffer: patch row i of crop b -> x[b*T + img_pos + i].  The CLS row lands on row img_pos-1 (the
+        # <im_start> slot, img_pos >= 1 because of BOS) and is overwritten by the embedding splice below.
+        assert img_pos >= 1
+        ops.gemm(ct, self.w.mm_w, out=x, bias=self.w.mm_b, rows_per_group=S, group_stride=T, group_offset=img_pos - 1)
         ops.embed_splice(input_ids.contiguous(), self.w.embed, x, img_pos, n_img)
         self._ensure_cache(B, self.max_tokens)
         self._llm_layers(x, B, T, 0, self.max_tokens)
