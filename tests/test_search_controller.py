@@ -1,0 +1,104 @@
+"""The product's iterative / batched search controller must expand nodes in exactly the reference's order.
+Pinned against the trajectories produced by the REAL reference visual_search() (tests/golden/search_*.npz).
+The heat-map sums are injected (tests/helpers.NumpyScorer) so this ordering logic is testable without a GPU;
+the CUDA scorer itself is covered by the gpu tests."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import NumpyScorer, StubVSM, synth_image
+from vstar_b200 import visual_search as VS
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("tag", ["stub_3lvl", "stub_default", "stub_weakcue"])
+def test_trajectory_matches_reference(tag):
+    g = np.load(os.path.join(G, f"search_{tag}.npz"))
+    img = synth_image(int(g["img_seed"]), int(g["w"]), int(g["h"]))
+    kw = json.loads(str(g["kw"]))
+    stub = StubVSM()
+    fs, pl, ok, av, st = VS.visual_search(stub, img, "mug", None, int(g["smallest"]), scorer=NumpyScorer(), return_state=True, **kw)
+    assert np.array_equal(np.array([s["bbox"] for s in st.search_path]), g["trajectory"])
+    assert np.array_equal(np.array(stub.calls), g["calls"])
+    assert pl == int(g["path_length"]) and int(ok) == int(g["success"])
+    assert list(fs["bbox"]) == list(g["final_bbox"])
+    assert np.allclose(fs["detection_result"].numpy(), g["detection_result"], rtol=0, atol=0)
+
+
+class BatchStub(StubVSM):
+    """same pure function, but through the batched entry point the CUDA VSM exposes"""
+
+    def __init__(self):
+        super().__init__()
+        self.batches = []
+
+    def detect_batch(self, images, questions):
+        self.batches.append(len(images))
+        out = []
+        for im in images:
+            boxes, logits, hm = StubVSM.inference(self, im, "", "detection")
+            ev = VS._NodeEval()
+            ev.n_logits = len(logits)
+            ev.top_logit = logits.view(-1).max()
+            ev.top_box = boxes[int(logits.view(-1).argmax())].clone()
+            ev.boxes, ev.scores, ev.full_map = boxes, logits, hm
+            out.append(ev)
+        return out
+
+
+@pytest.mark.parametrize("batch", [1, 4, 16])
+def test_speculative_batching_keeps_order(batch):
+    g = np.load(os.path.join(G, "search_stub_3lvl.npz"))
+    img = synth_image(int(g["img_seed"]), int(g["w"]), int(g["h"]))
+    kw = json.loads(str(g["kw"]))
+    stub = BatchStub()
+    fs, pl, ok, av, st = VS.visual_search(stub, img, "mug", None, int(g["smallest"]), scorer=NumpyScorer(), batch_size=batch,
+                                          return_state=True, **kw)
+    assert np.array_equal(np.array([s["bbox"] for s in st.search_path]), g["trajectory"])
+    assert pl == int(g["path_length"]) and list(fs["bbox"]) == list(g["final_bbox"])
+    assert max(stub.batches) <= batch
+    if batch > 1:
+        assert max(stub.batches) > 1          # speculation actually batches
+
+
+def test_many_searches_lockstep():
+    jobs, want = [], []
+    for tag in ["stub_3lvl", "stub_default"]:
+        g = np.load(os.path.join(G, f"search_{tag}.npz"))
+        kw = json.loads(str(g["kw"]))
+        if tag == "stub_default":
+            continue
+        for k in range(3):
+            jobs.append((synth_image(int(g["img_seed"]), int(g["w"]), int(g["h"])), "mug", int(g["smallest"])))
+            want.append(g["trajectory"])
+    stub = BatchStub()
+    res, states = VS.visual_search_many(stub, jobs, batch_size=8, scorer=NumpyScorer(), confidence_high=2.0)
+    for st, w in zip(states, want):
+        assert np.array_equal(np.array([s["bbox"] for s in st.search_path]), w)
+
+
+def test_deep_search_does_not_recurse():
+    """the reference hits Python's recursion limit near 990 expanded nodes"""
+    img = synth_image(5, 512, 512)
+    stub = BatchStub()
+    fs, pl, ok, av, st = VS.visual_search(stub, img, "mug", None, 10, scorer=NumpyScorer(), batch_size=64, confidence_high=2.0,
+                                          return_state=True)
+    assert len(st.search_path) == 1 + 4 + 16 + 64 + 256 + 1024 + 4096      # 512 -> 8 px leaves, > 990 expanded nodes
+
+
+def test_prompt_and_tokenizer_helpers():
+    from vstar_b200.config import tiny_config
+    from vstar_b200.vsm import SyntheticTokenizer, build_prompt, tokenizer_image_token
+    cfg = tiny_config()
+    tok = SyntheticTokenizer(cfg)
+    p = build_prompt("Please locate the mug in this image.")
+    assert p.startswith("A chat between") and p.endswith("ASSISTANT:") and "<im_start><image><im_end>\n" in p
+    ids = tokenizer_image_token(p, tok)
+    assert ids[0] == 1 and ids.count(-200) == 1
+    k = ids.index(-200)
+    assert ids[k - 1] == cfg.vocab - 2 and ids[k + 1] == cfg.vocab - 1
+    assert tok("Sure, [LOC].", add_special_tokens=False).input_ids.count(cfg.loc_token_idx) == 1
