@@ -97,6 +97,16 @@ int vsb_heatmap_bilinear_f32(const void* low, int LH, int LW, void* out, int h, 
 /* sums of the min-max-normalised heatmap over integer rectangles [x,y,w,h] (visual_search.py:255-266). */
 int vsb_rect_sums_f32(const void* hm, int h, int w, const void* rects_i32, int nrects, const void* stats3, void* out_f64, void* stream);
 
+/* Pillow-exact antialiased BICUBIC resize of a uint8 RGB crop resident on the device, in Pillow's two integer passes
+ * (libImaging/Resample.c 8bpc path; coefficient tables from vstar_b200/image.py), fused with /255, CLIP mean/std and the
+ * bf16 cast.  Replaces the per-crop host preprocessing of visual_search.py:186-194 (PIL crop, expand2square, HF
+ * CLIPImageProcessor / OwlViTProcessor resizes, .cuda(), .bfloat16()).  Virtual input = crop (cw x ch at x0,y0 of src)
+ * padded bottom/right with bg to in_w x in_h (expand2square, VisualSearch/utils/utils.py:28-39). */
+int vsb_resample_h_u8(const void* src, long long row_stride_bytes, int x0, int y0, int cw, int ch, int in_h, int bg0, int bg1, int bg2,
+                      const void* coefs_i32, const void* bounds_i32, int ksize, int out_w, void* tmp_u8, void* stream);
+int vsb_resample_v_u8(const void* tmp_u8, int out_w, const void* coefs_i32, const void* bounds_i32, int ksize, int out_h, void* out_u8,
+                      void* out_bf16_chw, void* out_f32_chw, const float* mean3_host, const float* std3_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

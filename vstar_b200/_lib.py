@@ -39,6 +39,8 @@ SIGNATURES = {
     "vsb_mask_dot_bf16": [c_p, c_p, c_p, c_i, c_ll, c_i, c_p],
     "vsb_heatmap_bilinear_f32": [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_p],
     "vsb_rect_sums_f32": [c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_p],
+    "vsb_resample_h_u8": [c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p],
+    "vsb_resample_v_u8": [c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p, ctypes.POINTER(c_f), ctypes.POINTER(c_f), c_p],
 }
 
 _lib = None

@@ -35,6 +35,23 @@ def _rows2d(t):
     return t.data_ptr(), t.shape[0], t.shape[1], t.stride(0)
 
 
+# optional per-launch profiling of the dominant kernel (bench.py roofline): CUDA events around every GEMM launch
+_prof = None
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> (total algorithmic flops, total ms, launches) over the GEMM launches since profile_begin()"""
+    global _prof
+    rec, _prof = _prof, None
+    torch.cuda.synchronize()
+    return sum(r[0] for r in rec), sum(r[1].elapsed_time(r[2]) for r in rec), len(rec)
+
+
 def gemm(a, w, out=None, bias=None, residual=None, epilogue=EPI_NONE, out_dtype=BF16, rows_per_group=0,
          group_stride=0, group_offset=0, out_rows=None):
     """out = epi(a @ w.T + bias) (+ residual).  a [M,K], w [N,K] bf16 (row stride arbitrary, inner stride 1)."""
@@ -54,9 +71,15 @@ def gemm(a, w, out=None, bias=None, residual=None, epilogue=EPI_NONE, out_dtype=
         _chk(bias, BF16)
         assert bias.numel() == N and bias.is_contiguous()
     _lib.launches += 1
+    if _prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     call("vsb_gemm_bf16", pa, lda, pw, ldw, out.data_ptr(), out.stride(0), M, N, K, _p(bias), _p(residual),
          residual.stride(0) if residual is not None else 0, epilogue, out_fp32, rows_per_group, group_stride, group_offset,
          _stream())
+    if _prof is not None:
+        e1.record()
+        _prof.append((2.0 * M * N * K, e0, e1))
     return out
 
 

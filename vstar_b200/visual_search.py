@@ -259,6 +259,7 @@ class SearchController:
         self.batch_size = max(1, int(batch_size))
         self.extract_noun_chunks = extract_noun_chunks
         self.batched = hasattr(vsm, "detect_batch")
+        self.regions = hasattr(vsm, "detect_regions")
 
     # -- evaluation ----------------------------------------------------------------------------------------
     def _evaluate(self, requests):
@@ -266,9 +267,11 @@ class SearchController:
         if not requests:
             return
         if self.batched:
-            crops = [st.crop(p) for st, p in requests]
             questions = [DETECTION_QUESTION.format(st.target) for st, p in requests]
-            results = self.vsm.detect_batch(crops, questions)
+            if self.regions:       # the crop is cut on the GPU from the resident search image
+                results = self.vsm.detect_regions([(st.image, p["bbox"]) for st, p in requests], questions)
+            else:
+                results = self.vsm.detect_batch([st.crop(p) for st, p in requests], questions)
             for (st, p), ev in zip(requests, results):
                 st.cache[st.key(p)] = ev
                 st.n_evals += 1

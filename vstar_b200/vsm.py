@@ -18,6 +18,7 @@ import torch
 from . import ops
 from .config import VSMConfig, IMAGE_TOKEN_INDEX
 from .engine import VSMEngine, VSMWeights
+from .image import GpuImagePipeline
 from .visual_search import (DEFAULT_IM_END_TOKEN, DEFAULT_IM_START_TOKEN, DEFAULT_IMAGE_TOKEN, Heatmap, CudaScorer, _NodeEval)
 
 BF = torch.bfloat16
@@ -164,7 +165,7 @@ class VSM:
     """Same surface as the reference wrapper: `VSM(args)`, `.inference(image, question, mode)`; plus `detect_batch`."""
 
     def __init__(self, args=None, engine: VSMEngine = None, tokenizer=None, frontier_batch=8, draft_answer="Sure, [LOC].",
-                 forced_answer_ids=None):
+                 forced_answer_ids=None, prep="gpu"):
         if engine is None:
             # visual_search.py:143-172: tokenizer + checkpoint from args.version, CLIP tower from args.vision_tower
             if args is None or not os.path.isdir(str(args.version)):
@@ -201,6 +202,12 @@ class VSM:
             self.draft_ids = list(forced_answer_ids)
         self._pinned = {}
         self.timers = dict(prep=0.0, engine=0.0)
+        # prep="gpu": crops are cut + resized on the device from the resident search image (Pillow-exact integer
+        # bicubic); prep="host": the reference's PIL path (kept for parity tests of the pipeline itself)
+        self.prep = prep
+        self.pipeline = GpuImagePipeline(engine.dev, self.cfg.clip_image, self.cfg.owl_image) if prep == "gpu" else None
+        self._resident = {}          # id(PIL image) -> (PIL image, uint8 HWC device tensor)
+        self.h2d_bytes = 0
 
     # ------------------------------------------------------------------ host prep
     def _staging(self, B):
@@ -211,14 +218,48 @@ class VSM:
         return self._pinned[B]
 
     def _prep(self, images):
+        """host path: PIL crops -> (clip [B,3,224,224], owl [B,3,768,768]) bf16 on the device"""
         c = self.cfg
         B = len(images)
         pc, po = self._staging(B)
         for i, im in enumerate(images):
             preprocess_clip_into(im, pc[i], c.clip_image)
             preprocess_owl_into(im, po[i], c.owl_image)
+        self.h2d_bytes += pc.numel() * 4 + po.numel() * 4
         ic = ops.cast_f32_bf16(pc.cuda(non_blocking=True))      # .bfloat16() of the reference (visual_search.py:189,194)
         io = ops.cast_f32_bf16(po.cuda(non_blocking=True))
+        return ic, io
+
+    def resident(self, pil_img):
+        """uint8 HWC copy of a search image in HBM (uploaded once, reused by every crop of that search)"""
+        key = id(pil_img)
+        hit = self._resident.get(key)
+        if hit is None or hit[0] is not pil_img:
+            if len(self._resident) >= 64:
+                self._resident.pop(next(iter(self._resident)))
+            t = self.pipeline.upload(pil_img)
+            self.h2d_bytes += t.numel()
+            self._resident[key] = (pil_img, t)
+            return t
+        return hit[1]
+
+    def release(self, pil_img=None):
+        if pil_img is None:
+            self._resident.clear()
+        else:
+            self._resident.pop(id(pil_img), None)
+
+    def _prep_regions(self, regions):
+        """regions: list of (source PIL image, bbox [x,y,w,h]) -> device pixel tensors via the GPU image pipeline"""
+        if self.prep != "gpu":
+            crops = [src.crop((int(b[0]), int(b[1]), int(b[0] + b[2]), int(b[1] + b[3]))) for src, b in regions]
+            return self._prep(crops)
+        c = self.cfg
+        B = len(regions)
+        ic = torch.empty((B, 3, c.clip_image, c.clip_image), dtype=BF, device=self.engine.dev)
+        io = torch.empty((B, 3, c.owl_image, c.owl_image), dtype=BF, device=self.engine.dev)
+        for i, (src, b) in enumerate(regions):
+            self.pipeline.crop_tensors(self.resident(src), b, ic[i], io[i])
         return ic, io
 
     def _ids(self, question):
@@ -226,17 +267,17 @@ class VSM:
         return tokenizer_image_token(prompt, self.vsm_tokenizer)
 
     # ------------------------------------------------------------------ engine calls
-    def _run(self, images, questions, mode):
-        """-> list (per crop) of dicts with device tensors"""
+    def _run(self, regions, questions, mode):
+        """regions: list of (source PIL image, bbox) -> list (per crop) of dicts with device tensors"""
         import time
         t0 = time.perf_counter()
         ids_list = [self._ids(q) for q in questions]
         groups = {}
         for i, ids in enumerate(ids_list):
             groups.setdefault((len(ids), ids.index(IMAGE_TOKEN_INDEX)), []).append(i)
-        results = [None] * len(images)
+        results = [None] * len(regions)
         for key, members in groups.items():
-            ic, io = self._prep([images[i] for i in members])
+            ic, io = self._prep_regions([regions[i] for i in members])
             t1 = time.perf_counter()
             self.timers["prep"] += t1 - t0
             prompt = torch.tensor([ids_list[i] for i in members], dtype=torch.int64)
@@ -285,7 +326,9 @@ class VSM:
     def inference(self, image, question, mode="segmentation"):
         """visual_search.py:174-225.  'segmentation' -> Heatmap-backed fp32 tensor [h,w] on GPU (>= 0);
         'vqa' -> str; 'detection' -> (boxes [P,4] CPU, scores [P,1] CPU, heatmap [h,w] GPU)."""
-        r = self._run([image], [question], mode)[0]
+        r = self._run([(image, [0, 0, image.width, image.height])], [question], mode)[0]
+        if self.prep == "gpu":
+            self.release(image)           # a crop handed in by a caller is not a long-lived search image
         if mode == "vqa":
             input_len = len(self._ids(question))
             text = self.vsm_tokenizer.batch_decode(r["output_ids"][input_len:].view(1, -1), skip_special_tokens=True)[0]
@@ -296,10 +339,14 @@ class VSM:
             return heat.map
         return r["boxes"].cpu(), r["scores"].view(-1, 1).cpu(), heat.map
 
-    @torch.inference_mode()
     def detect_batch(self, images, questions):
-        """Batched detection-mode evaluation for the search controller -> list of _NodeEval."""
-        rs = self._run(images, questions, "detection")
+        """PIL crops in, see detect_regions"""
+        return self.detect_regions([(im, [0, 0, im.width, im.height]) for im in images], questions)
+
+    @torch.inference_mode()
+    def detect_regions(self, regions, questions):
+        """Batched detection-mode evaluation for the search controller: regions = [(search image, bbox)] -> [_NodeEval]."""
+        rs = self._run(regions, questions, "detection")
         sc = torch.stack([r["scores"] for r in rs])                          # [n, P]
         idx, val = ops.argmax_rows(sc.contiguous())
         bx = torch.stack([r["boxes"] for r in rs])                           # [n, P, 4]
