@@ -40,8 +40,10 @@ int vsb_version(void);
 int vsb_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
                   const void* bias, const void* residual, long long ldr, int epilogue, int out_fp32, int rows_per_group,
                   long long group_stride, long long group_offset, void* stream);
-/* testing / tuning hook: force tile width (64/128/256, 0 = auto) and CTA count (0 = #SMs) */
+/* testing / tuning hooks: force the kernel variant (64/128/256 = single-CTA tile width, 512 = 2-CTA cta_group::2
+ * 256x256 cluster tiles, 0 = auto) and the CTA count (0 = #SMs); tile-rasterisation band height in m-blocks (0 = auto) */
 int vsb_gemm_set_tuning(int force_bn, int max_ctas);
+int vsb_gemm_set_group_m(int group_m);
 
 /* nn.LayerNorm over the last dim (fp32 stats), optional fused activation (VSB_EPI_NONE / VSB_EPI_GELU).
  * HF CLIP/OWL layer_norm1/2, pre/post layernorm; SAM norm1-4, norm_final_attn; LayerNorm2d in NHWC (common.py:31-43). */
@@ -95,7 +97,8 @@ int vsb_mask_dot_bf16(const void* up, const void* hyper, void* out, int B, long 
  * plus (max,min,sum) (VSM.py:534-537; visual_search.py:223-224, :268-275, :420-421). */
 int vsb_heatmap_bilinear_f32(const void* low, int LH, int LW, void* out, int h, int w, int do_clamp, void* scratch, void* stats3, void* stream);
 /* sums of the min-max-normalised heatmap over integer rectangles [x,y,w,h] (visual_search.py:255-266). */
-int vsb_rect_sums_f32(const void* hm, int h, int w, const void* rects_i32, int nrects, const void* stats3, void* out_f64, void* stream);
+int vsb_rect_sums_f32(const void* hm, int h, int w, const void* rects_i32, int nrects, const void* stats3, void* out_f64,
+                      void* scratch_f64 /* 64*nrects doubles */, void* stream);
 
 /* Pillow-exact antialiased BICUBIC resize of a uint8 RGB crop resident on the device, in Pillow's two integer passes
  * (libImaging/Resample.c 8bpc path; coefficient tables from vstar_b200/image.py), fused with /255, CLIP mean/std and the

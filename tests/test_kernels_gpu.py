@@ -60,6 +60,55 @@ def test_gemm_forced_tile(ops, bn):
     assert torch.allclose(out, ref, rtol=1e-4, atol=1e-3), rel_err(out, ref)
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 512, 256), (2560, 4096, 512), (300, 514, 768), (1000, 1280, 320),
+                                   (129, 257, 128), (2048, 11008, 256), (4096, 768, 768)])
+def test_gemm_2cta(ops, M, N, K):
+    """cta_group::2 kernel (256x256 cluster tiles) on even / ragged shapes"""
+    from vstar_b200 import _lib
+    a, w, b, r = rnd(M, K, seed=31), rnd(N, K, scale=1 / math.sqrt(K), seed=32), rnd(N, seed=33), rnd(M, N, seed=34)
+    _lib.call("vsb_gemm_set_tuning", 512, 0)
+    try:
+        out = ops.gemm(a, w, out_dtype=torch.float32)
+        out2 = ops.gemm(a, w, bias=b, residual=r, epilogue=ops.EPI_QUICK_GELU)
+    finally:
+        _lib.call("vsb_gemm_set_tuning", 0, 0)
+    ref = a.float() @ w.float().t()
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-3), rel_err(out, ref)
+    y = ref + b.float()
+    ref2 = y * torch.sigmoid(1.702 * y) + r.float()
+    assert torch.allclose(out2.float(), ref2, rtol=1e-2, atol=3e-2), rel_err(out2, ref2)
+
+
+def test_gemm_2cta_persistent_few_clusters(ops):
+    from vstar_b200 import _lib
+    M, N, K = 1536, 2048, 448
+    a, w = rnd(M, K, seed=35), rnd(N, K, scale=1 / math.sqrt(K), seed=36)
+    _lib.call("vsb_gemm_set_tuning", 512, 6)          # 3 clusters, 48 tiles -> 16 tiles each: ring + TMEM double-buffer phases
+    try:
+        out = ops.gemm(a, w, out_dtype=torch.float32)
+    finally:
+        _lib.call("vsb_gemm_set_tuning", 0, 0)
+    ref = a.float() @ w.float().t()
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-3), rel_err(out, ref)
+
+
+@pytest.mark.parametrize("group_m", [1, 3, 8, 64])
+def test_gemm_tile_rasterisation(ops, group_m):
+    from vstar_b200 import _lib
+    M, N, K = 1500, 1300, 192
+    a, w = rnd(M, K, seed=37), rnd(N, K, scale=1 / math.sqrt(K), seed=38)
+    _lib.call("vsb_gemm_set_group_m", group_m)
+    try:
+        out = ops.gemm(a, w, out_dtype=torch.float32)
+        _lib.call("vsb_gemm_set_tuning", 512, 0)
+        out2 = ops.gemm(a, w, out_dtype=torch.float32)
+    finally:
+        _lib.call("vsb_gemm_set_group_m", 0)
+        _lib.call("vsb_gemm_set_tuning", 0, 0)
+    ref = a.float() @ w.float().t()
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-3) and torch.allclose(out2, ref, rtol=1e-4, atol=1e-3)
+
+
 def test_gemm_persistent_many_tiles(ops):
     """few CTAs, many tiles per CTA: exercises the smem ring phases and the TMEM double buffer"""
     from vstar_b200 import _lib

@@ -6,7 +6,7 @@ import math
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from vstar_b200 import ops
+from vstar_b200 import ops, _lib
 
 BF = torch.bfloat16
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.int8, device="cuda")
@@ -42,7 +42,12 @@ def main():
         ms = timeit(lambda: ops.gemm(a, w, out=out))
         ms_t = timeit(lambda: torch.matmul(a, w.t(), out=out))
         tf = 2 * M * N * K / ms / 1e9
-        res.append(dict(kernel="gemm", name=name, M=M, N=N, K=K, ms=ms, tflops=tf, torch_ms=ms_t, torch_tflops=2 * M * N * K / ms_t / 1e9))
+        var = {}
+        for tag, bn in (("1cta_256", 256), ("1cta_128", 128), ("2cta", 512)):
+            _lib.call("vsb_gemm_set_tuning", bn, 0)
+            var[tag] = round(2 * M * N * K / timeit(lambda: ops.gemm(a, w, out=out)) / 1e9, 1)
+        _lib.call("vsb_gemm_set_tuning", 0, 0)
+        res.append(dict(kernel="gemm", name=name, M=M, N=N, K=K, ms=ms, tflops=tf, torch_ms=ms_t, torch_tflops=2 * M * N * K / ms_t / 1e9, variants=var))
         print(res[-1], flush=True)
     for B, H, S, D, causal, name in [(8, 32, 320, 128, True, "llama prefill B=8"), (8, 12, 2305, 64, False, "owl B=8"),
                                      (8, 16, 257, 64, False, "clip B=8"), (64, 32, 320, 128, True, "llama prefill B=64")]:

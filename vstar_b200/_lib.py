@@ -18,6 +18,7 @@ c_f = ctypes.c_float
 SIGNATURES = {
     "vsb_gemm_bf16": [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_p, c_p, c_ll, c_i, c_i, c_i, c_ll, c_ll, c_p],
     "vsb_gemm_set_tuning": [c_i, c_i],
+    "vsb_gemm_set_group_m": [c_i],
     "vsb_layernorm_bf16": [c_p, c_ll, c_p, c_p, c_p, c_ll, c_i, c_i, c_f, c_i, c_p],
     "vsb_rmsnorm_bf16": [c_p, c_ll, c_p, c_p, c_ll, c_i, c_i, c_f, c_p],
     "vsb_rope_bf16": [c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_ll, c_ll, c_p],
@@ -38,7 +39,7 @@ SIGNATURES = {
     "vsb_im2col3x3_nhwc_bf16": [c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "vsb_mask_dot_bf16": [c_p, c_p, c_p, c_i, c_ll, c_i, c_p],
     "vsb_heatmap_bilinear_f32": [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_p],
-    "vsb_rect_sums_f32": [c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_p],
+    "vsb_rect_sums_f32": [c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p],
     "vsb_resample_h_u8": [c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p],
     "vsb_resample_v_u8": [c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p, ctypes.POINTER(c_f), ctypes.POINTER(c_f), c_p],
 }

@@ -48,16 +48,16 @@ struct AttnParams {
   float scale_log2;
 };
 
-constexpr int FA_BM = 64, FA_BN = 64;
+constexpr int FA_BN = 64;
 
 // swizzled element offset of (row, 16B-chunk) in a [rows][D] bf16 tile
 template <int D>
 __device__ __forceinline__ int swz(int row, int chunk) { return row * D + ((chunk ^ (row & 7)) << 3); }
 
-template <int D>
+template <int D, int ROWS>
 __device__ __forceinline__ void load_tile(bf16* s, const bf16* g, long long rs, int row0, int nrows_valid, int tid) {
   constexpr int CH = D / 8;
-  for (int i = tid; i < FA_BN * CH; i += 128) {
+  for (int i = tid; i < ROWS * CH; i += 128) {
     const int r = i / CH, c = i - r * CH;
     const bool ok = (row0 + r) < nrows_valid;
     const int rr = ok ? (row0 + r) : 0;
@@ -65,17 +65,20 @@ __device__ __forceinline__ void load_tile(bf16* s, const bf16* g, long long rs, 
   }
 }
 
-template <int D>
+// MT = m16 tiles per warp: a CTA (4 warps) owns BM = 64*MT query rows; each K/V fragment loaded from shared memory
+// (ldmatrix) is reused by the MT row tiles of the warp, halving shared-memory traffic per flop at MT = 2.
+template <int D, int MT>
 __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnParams p) {
+  constexpr int BM = 64 * MT;
   extern __shared__ __align__(128) uint8_t fa_smem[];
   bf16* sQ = reinterpret_cast<bf16*>(fa_smem);
-  bf16* sK = sQ + FA_BM * D;            // [2][64][D]
+  bf16* sK = sQ + BM * D;               // [2][64][D]
   bf16* sV = sK + 2 * FA_BN * D;        // [2][64][D]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int m_blk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int q0 = m_blk * FA_BM;
+  const int q0 = m_blk * BM;
   const bf16* qg = p.q + (long long)b * p.q_bs + (long long)h * D;
   const bf16* kg = p.k + (long long)b * p.k_bs + (long long)h * D;
   const bf16* vg = p.v + (long long)b * p.v_bs + (long long)h * D;
@@ -83,109 +86,120 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnParams p) {
 
   int n_blocks = (p.Sk + FA_BN - 1) / FA_BN;
   if (p.causal) {
-    int last_key = q0 + FA_BM - 1 + off;            // largest key any query of this tile may see
+    int last_key = q0 + BM - 1 + off;               // largest key any query of this tile may see
     if (last_key > p.Sk - 1) last_key = p.Sk - 1;
     if (last_key < 0) last_key = 0;
     const int nb = last_key / FA_BN + 1;
     if (nb < n_blocks) n_blocks = nb;
   }
 
-  load_tile<D>(sQ, qg, p.q_rs, q0, p.Sq, tid);
-  load_tile<D>(sK, kg, p.k_rs, 0, p.Sk, tid);
-  load_tile<D>(sV, vg, p.v_rs, 0, p.Sk, tid);
+  load_tile<D, BM>(sQ, qg, p.q_rs, q0, p.Sq, tid);
+  load_tile<D, FA_BN>(sK, kg, p.k_rs, 0, p.Sk, tid);
+  load_tile<D, FA_BN>(sV, vg, p.v_rs, 0, p.Sk, tid);
   cp_async_commit();
 
-  uint32_t qf[D / 16][4];
-  float o_acc[D / 8][4];
+  uint32_t qf[MT][D / 16][4];
+  float o_acc[MT][D / 8][4];
 #pragma unroll
-  for (int i = 0; i < D / 8; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f; }
-  float row_max[2] = {-INFINITY, -INFINITY};
-  float row_sum[2] = {0.f, 0.f};
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) { o_acc[mt][i][0] = o_acc[mt][i][1] = o_acc[mt][i][2] = o_acc[mt][i][3] = 0.f; }
+  float row_max[MT][2], row_sum[MT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) { row_max[mt][0] = row_max[mt][1] = -INFINITY; row_sum[mt][0] = row_sum[mt][1] = 0.f; }
+  const int wrow = warp * 16 * MT;      // this warp's first query row inside the CTA tile
 
   for (int nb = 0; nb < n_blocks; ++nb) {
     const int buf = nb & 1;
     cp_async_wait<0>();
     __syncthreads();
     if (nb + 1 < n_blocks) {
-      load_tile<D>(sK + (buf ^ 1) * FA_BN * D, kg, p.k_rs, (nb + 1) * FA_BN, p.Sk, tid);
-      load_tile<D>(sV + (buf ^ 1) * FA_BN * D, vg, p.v_rs, (nb + 1) * FA_BN, p.Sk, tid);
+      load_tile<D, FA_BN>(sK + (buf ^ 1) * FA_BN * D, kg, p.k_rs, (nb + 1) * FA_BN, p.Sk, tid);
+      load_tile<D, FA_BN>(sV + (buf ^ 1) * FA_BN * D, vg, p.v_rs, (nb + 1) * FA_BN, p.Sk, tid);
       cp_async_commit();
     }
     if (nb == 0) {
 #pragma unroll
-      for (int kk = 0; kk < D / 16; ++kk)
-        ldmatrix_x4(qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], smem_u32(sQ + swz<D>(warp * 16 + (lane & 15), kk * 2 + (lane >> 4))));
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          ldmatrix_x4(qf[mt][kk][0], qf[mt][kk][1], qf[mt][kk][2], qf[mt][kk][3],
+                      smem_u32(sQ + swz<D>(wrow + mt * 16 + (lane & 15), kk * 2 + (lane >> 4))));
     }
     const bf16* cK = sK + buf * FA_BN * D;
     const bf16* cV = sV + buf * FA_BN * D;
 
-    // ---- S = Q K^T : 16 x 64 per warp
-    float s[8][4];
+    // ---- S = Q K^T : (16*MT) x 64 per warp
+    float s[MT][8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[mt][i][0] = s[mt][i][1] = s[mt][i][2] = s[mt][i][3] = 0.f; }
 #pragma unroll
     for (int kk = 0; kk < D / 16; ++kk) {
 #pragma unroll
       for (int np = 0; np < 4; ++np) {
         uint32_t r0, r1, r2, r3;
         ldmatrix_x4(r0, r1, r2, r3, smem_u32(cK + swz<D>(np * 16 + (lane & 7) + ((lane >> 4) << 3), kk * 2 + ((lane >> 3) & 1))));
-        mma_bf16_16816(s[2 * np], qf[kk], r0, r1);
-        mma_bf16_16816(s[2 * np + 1], qf[kk], r2, r3);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma_bf16_16816(s[mt][2 * np], qf[mt][kk], r0, r1);
+          mma_bf16_16816(s[mt][2 * np + 1], qf[mt][kk], r2, r3);
+        }
       }
     }
-    // ---- scale, mask, online softmax (rows g and g+8 of this warp's 16)
+    // ---- scale, mask, online softmax (rows g and g+8 of each 16-row tile)
     const int key0 = nb * FA_BN;
-    const int qrow0 = q0 + warp * 16 + g;
-    float mx[2] = {-INFINITY, -INFINITY};
+    uint32_t pf[MT][4][4];   // P as A-fragments for 4 k16 steps over the 64 keys
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int mt = 0; mt < MT; ++mt) {
+      const int qrow0 = q0 + wrow + mt * 16 + g;
+      float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = key0 + i * 8 + 2 * t + (e & 1);
-        const int qr = qrow0 + ((e >> 1) << 3);
-        float x = s[i][e] * p.scale_log2;
-        const bool masked = (key >= p.Sk) || (p.causal && key > qr + off);
-        x = masked ? -INFINITY : x;
-        s[i][e] = x;
-        mx[e >> 1] = fmaxf(mx[e >> 1], x);
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = key0 + i * 8 + 2 * t + (e & 1);
+          const int qr = qrow0 + ((e >> 1) << 3);
+          float x = s[mt][i][e] * p.scale_log2;
+          const bool masked = (key >= p.Sk) || (p.causal && key > qr + off);
+          x = masked ? -INFINITY : x;
+          s[mt][i][e] = x;
+          mx[e >> 1] = fmaxf(mx[e >> 1], x);
+        }
       }
-    }
-    float corr[2], mnew[2];
+      float corr[2], mnew[2];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      float m = mx[r];
-      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-      mnew[r] = fmaxf(row_max[r], m);
-      const float msafe = (mnew[r] == -INFINITY) ? 0.f : mnew[r];
-      corr[r] = exp2f(row_max[r] - msafe);     // row_max = -inf -> 0
-      row_max[r] = mnew[r];
-      mnew[r] = msafe;
-    }
-    float psum[2] = {0.f, 0.f};
-    uint32_t pf[4][4];   // P as A-fragments for 4 k16 steps over the 64 keys
+      for (int r = 0; r < 2; ++r) {
+        float m = mx[r];
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        mnew[r] = fmaxf(row_max[mt][r], m);
+        const float msafe = (mnew[r] == -INFINITY) ? 0.f : mnew[r];
+        corr[r] = exp2f(row_max[mt][r] - msafe);     // row_max = -inf -> 0
+        row_max[mt][r] = mnew[r];
+        mnew[r] = msafe;
+      }
+      float psum[2] = {0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float p0 = exp2f(s[i][0] - mnew[0]);
-      const float p1 = exp2f(s[i][1] - mnew[0]);
-      const float p2 = exp2f(s[i][2] - mnew[1]);
-      const float p3 = exp2f(s[i][3] - mnew[1]);
-      // the reference casts softmax output to bf16 before P@V; sum the *rounded* values so P rows sum to the normaliser
-      const uint32_t lo = pack_bf16x2(p0, p1);
-      const uint32_t hi = pack_bf16x2(p2, p3);
-      float2 a = unpack_bf16x2(lo), c = unpack_bf16x2(hi);
-      psum[0] += p0 + p1;
-      psum[1] += p2 + p3;
-      (void)a; (void)c;
-      pf[i >> 1][(i & 1) * 2 + 0] = lo;
-      pf[i >> 1][(i & 1) * 2 + 1] = hi;
-    }
+      for (int i = 0; i < 8; ++i) {
+        const float p0 = exp2f(s[mt][i][0] - mnew[0]);
+        const float p1 = exp2f(s[mt][i][1] - mnew[0]);
+        const float p2 = exp2f(s[mt][i][2] - mnew[1]);
+        const float p3 = exp2f(s[mt][i][3] - mnew[1]);
+        psum[0] += p0 + p1;
+        psum[1] += p2 + p3;
+        // the reference casts the softmax output to bf16 before P@V
+        pf[mt][i >> 1][(i & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+        pf[mt][i >> 1][(i & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+      }
 #pragma unroll
-    for (int r = 0; r < 2; ++r) row_sum[r] = row_sum[r] * corr[r] + psum[r];
+      for (int r = 0; r < 2; ++r) row_sum[mt][r] = row_sum[mt][r] * corr[r] + psum[r];
 #pragma unroll
-    for (int i = 0; i < D / 8; ++i) {
-      o_acc[i][0] *= corr[0]; o_acc[i][1] *= corr[0];
-      o_acc[i][2] *= corr[1]; o_acc[i][3] *= corr[1];
+      for (int i = 0; i < D / 8; ++i) {
+        o_acc[mt][i][0] *= corr[0]; o_acc[mt][i][1] *= corr[0];
+        o_acc[mt][i][2] *= corr[1]; o_acc[mt][i][3] *= corr[1];
+      }
     }
     // ---- O += P V
 #pragma unroll
@@ -194,31 +208,38 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnParams p) {
       for (int dp = 0; dp < D / 16; ++dp) {
         uint32_t r0, r1, r2, r3;
         ldmatrix_x4_trans(r0, r1, r2, r3, smem_u32(cV + swz<D>(ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), dp * 2 + (lane >> 4))));
-        mma_bf16_16816(o_acc[2 * dp], pf[ks], r0, r1);
-        mma_bf16_16816(o_acc[2 * dp + 1], pf[ks], r2, r3);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma_bf16_16816(o_acc[mt][2 * dp], pf[mt][ks], r0, r1);
+          mma_bf16_16816(o_acc[mt][2 * dp + 1], pf[mt][ks], r2, r3);
+        }
       }
     }
   }
 
   // ---- finalize: O /= row_sum, stage through smem (reuse sQ), coalesced 16 B stores
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    float sum = row_sum[r];
-    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-    row_sum[r] = (sum > 0.f) ? 1.f / sum : 0.f;
-  }
   __syncthreads();   // everyone is done reading sQ fragments / K / V
 #pragma unroll
-  for (int i = 0; i < D / 8; ++i) {
-    const int r_lo = warp * 16 + g, r_hi = r_lo + 8;
-    *reinterpret_cast<uint32_t*>(sQ + swz<D>(r_lo, i) + 2 * t) = pack_bf16x2(o_acc[i][0] * row_sum[0], o_acc[i][1] * row_sum[0]);
-    *reinterpret_cast<uint32_t*>(sQ + swz<D>(r_hi, i) + 2 * t) = pack_bf16x2(o_acc[i][2] * row_sum[1], o_acc[i][3] * row_sum[1]);
+  for (int mt = 0; mt < MT; ++mt) {
+    float inv[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float sum = row_sum[mt][r];
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      inv[r] = (sum > 0.f) ? 1.f / sum : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) {
+      const int r_lo = wrow + mt * 16 + g, r_hi = r_lo + 8;
+      *reinterpret_cast<uint32_t*>(sQ + swz<D>(r_lo, i) + 2 * t) = pack_bf16x2(o_acc[mt][i][0] * inv[0], o_acc[mt][i][1] * inv[0]);
+      *reinterpret_cast<uint32_t*>(sQ + swz<D>(r_hi, i) + 2 * t) = pack_bf16x2(o_acc[mt][i][2] * inv[1], o_acc[mt][i][3] * inv[1]);
+    }
   }
   __syncthreads();
   bf16* og = p.o + (long long)b * p.o_bs + (long long)h * D;
   constexpr int CH = D / 8;
-  for (int i = tid; i < FA_BM * CH; i += 128) {
+  for (int i = tid; i < BM * CH; i += 128) {
     const int r = i / CH, c = i - r * CH;
     if (q0 + r < p.Sq) *reinterpret_cast<uint4*>(og + (long long)(q0 + r) * p.o_rs + c * 8) = *reinterpret_cast<const uint4*>(sQ + swz<D>(r, c));
   }
@@ -309,18 +330,29 @@ extern "C" int vsb_flash_attn_bf16(const void* q, const void* k, const void* v, 
   p.q_bs = q_bs; p.q_rs = q_rs; p.k_bs = k_bs; p.k_rs = k_rs; p.v_bs = v_bs; p.v_rs = v_rs; p.o_bs = o_bs; p.o_rs = o_rs;
   p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk; p.causal = causal;
   p.scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid((Sq + FA_BM - 1) / FA_BM, H, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (D == 64) {
-    const int smem = (FA_BM + 4 * FA_BN) * 64 * 2;
-    static bool set64 = false;
-    if (!set64) { VSB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set64 = true; }
-    flash_attn_kernel<64><<<grid, 128, smem, st>>>(p);
+    // 128 query rows per CTA (2 m16 tiles per warp) once there are enough rows to fill them
+    if (false && Sq > 64) {   // MT=2 measured SLOWER on B200 (218 regs -> half the occupancy): 155 vs 182 TFLOP/s on OWL shapes
+      constexpr int BMq = 128;
+      const int smem = (BMq + 4 * FA_BN) * 64 * 2;
+      static bool set64b = false;
+      if (!set64b) { VSB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set64b = true; }
+      dim3 grid((Sq + BMq - 1) / BMq, H, B);
+      flash_attn_kernel<64, 2><<<grid, 128, smem, st>>>(p);
+    } else {
+      const int smem = (64 + 4 * FA_BN) * 64 * 2;
+      static bool set64 = false;
+      if (!set64) { VSB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set64 = true; }
+      dim3 grid((Sq + 63) / 64, H, B);
+      flash_attn_kernel<64, 1><<<grid, 128, smem, st>>>(p);
+    }
   } else {
-    const int smem = (FA_BM + 4 * FA_BN) * 128 * 2;
+    const int smem = (64 + 4 * FA_BN) * 128 * 2;
     static bool set128 = false;
-    if (!set128) { VSB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set128 = true; }
-    flash_attn_kernel<128><<<grid, 128, smem, st>>>(p);
+    if (!set128) { VSB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set128 = true; }
+    dim3 grid((Sq + 63) / 64, H, B);
+    flash_attn_kernel<128, 1><<<grid, 128, smem, st>>>(p);
   }
   VSB_LAUNCH_CHECK();
   return VSB_OK;

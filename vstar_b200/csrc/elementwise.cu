@@ -133,21 +133,29 @@ __global__ void rope_kernel(bf16* __restrict__ qkv, long long ld, int rows, int 
   if (row >= rows) return;
   const int pos = positions ? positions[row] : pos0 + (row % T);
   const int half = D >> 1;
+  const int hv = half >> 3;                 // 16-byte vectors per half head
   bf16* base = qkv + ((long long)(row / T) * group_stride + group_offset + (row % T)) * ld;
   const bf16* cr = cos_t + (long long)pos * half;
   const bf16* sr = sin_t + (long long)pos * half;
-  for (int idx = threadIdx.x; idx < 2 * H * half; idx += blockDim.x) {
-    const int which = idx / (H * half);         // 0 = q, 1 = k
-    const int rem = idx - which * H * half;
-    const int h = rem / half;
-    const int i = rem - h * half;
-    const float cs = bf2f(cr[i]);
-    const float sn = bf2f(sr[i]);
-    bf16* p = base + (long long)which * H * D + h * D;
-    const float x1 = bf2f(p[i]);
-    const float x2 = bf2f(p[i + half]);
-    p[i] = f2bf(rbf(x1 * cs) + rbf(-x2 * sn));
-    p[i + half] = f2bf(rbf(x2 * cs) + rbf(x1 * sn));
+  // one thread = 8 consecutive (i, i+half) pairs of one head of q or k
+  for (int idx = threadIdx.x; idx < 2 * H * hv; idx += blockDim.x) {
+    const int hh = idx / hv;                // 0..2H-1 : q heads then k heads (contiguous: k starts at H*D)
+    const int v = idx - hh * hv;
+    bf16* p = base + (long long)hh * D + v * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(p);
+    const uint4 b = *reinterpret_cast<const uint4*>(p + half);
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(cr + v * 8));
+    const uint4 s = __ldg(reinterpret_cast<const uint4*>(sr + v * 8));
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, cw[4] = {c.x, c.y, c.z, c.w}, sw[4] = {s.x, s.y, s.z, s.w};
+    uint32_t oa[4], ob[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x1 = unpack_bf16x2(aw[j]), x2 = unpack_bf16x2(bw[j]), cs = unpack_bf16x2(cw[j]), sn = unpack_bf16x2(sw[j]);
+      oa[j] = pack_bf16x2(rbf(x1.x * cs.x) + rbf(-x2.x * sn.x), rbf(x1.y * cs.y) + rbf(-x2.y * sn.y));
+      ob[j] = pack_bf16x2(rbf(x2.x * cs.x) + rbf(x1.x * sn.x), rbf(x2.y * cs.y) + rbf(x1.y * sn.y));
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
+    *reinterpret_cast<uint4*>(p + half) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
   }
 }
 
@@ -345,7 +353,7 @@ extern "C" int vsb_rmsnorm_bf16(const void* x, long long ldx, const void* w, voi
 extern "C" int vsb_rope_bf16(void* qkv, long long ld, int rows, int T, int H, int D, int pos0, const void* cos_table,
                              const void* sin_table, const void* positions, long long group_stride, long long group_offset,
                              void* stream) {
-  VSB_CHECK_ARG(qkv && cos_table && sin_table && rows >= 0 && T > 0 && H > 0 && D % 2 == 0, "vsb_rope_bf16: bad args");
+  VSB_CHECK_ARG(qkv && cos_table && sin_table && rows >= 0 && T > 0 && H > 0 && D % 16 == 0 && ld % 8 == 0, "vsb_rope_bf16: bad args (D % 16, ld % 8)");
   if (rows == 0) return VSB_OK;
   rope_kernel<<<rows, 256, 0, STREAM(stream)>>>((bf16*)qkv, ld, rows, T, H, D, pos0, (const bf16*)cos_table, (const bf16*)sin_table,
                                                 (const int*)positions, group_stride, group_offset);

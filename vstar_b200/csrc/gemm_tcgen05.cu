@@ -39,6 +39,7 @@ struct GemmParams {
   int rows_per_group;  // output row remap: r = (m / rpg) * group_stride + group_offset + m % rpg
   long long group_stride, group_offset;
   int tiles_m, tiles_n;
+  int group_m;         // tile rasterisation band height (in m-blocks)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -160,6 +161,118 @@ __device__ __forceinline__ float apply_act(float x, int epi) {
   }
 }
 
+// tile rasterisation: groups of GROUP_M m-blocks x all n-blocks, m fastest inside a group, so that the CTAs running
+// concurrently share both A and W tiles in L2 (instead of one W tile and 148 distinct A tiles)
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int group_m, int& m_blk, int& n_blk) {
+  const int per_group = group_m * tiles_n;
+  const int g = t / per_group;
+  const int first_m = g * group_m;
+  const int gsize = min(group_m, tiles_m - first_m);
+  const int r = t - g * per_group;
+  m_blk = first_m + r % gsize;
+  n_blk = r / gsize;
+}
+
+// ---------------------------------------------------------------- shared epilogue: 32 fp32 accumulator columns of one row
+// bias -> activation / SwiGLU -> (+residual) -> bf16 / fp32 store (16 B vector stores when aligned)
+__device__ __forceinline__ void epilogue_store(const GemmParams& p, const uint32_t* v, long long orow, int n0, bool swiglu) {
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (p.bias != nullptr) {
+      if (n0 + 32 <= p.N) {
+        const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          uint4 b = __ldg(bp + j4);
+          float2 t;
+          t = unpack_bf16x2(b.x); f[j4 * 8 + 0] += t.x; f[j4 * 8 + 1] += t.y;
+          t = unpack_bf16x2(b.y); f[j4 * 8 + 2] += t.x; f[j4 * 8 + 3] += t.y;
+          t = unpack_bf16x2(b.z); f[j4 * 8 + 4] += t.x; f[j4 * 8 + 5] += t.y;
+          t = unpack_bf16x2(b.w); f[j4 * 8 + 6] += t.x; f[j4 * 8 + 7] += t.y;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + j < p.N) f[j] += bf2f(p.bias[n0 + j]);
+      }
+    }
+    if (swiglu) {
+      // interleaved weight rows: even column = gate_j, odd column = up_j -> out column (n0/2 + j)
+      const int on0 = n0 >> 1;
+      const int nout = p.N >> 1;
+      float o[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = silu_f(f[2 * j]) * f[2 * j + 1];
+      bf16* crow = reinterpret_cast<bf16*>(p.C) + orow * p.ldc + on0;
+      if (on0 + 16 <= nout && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+        uint4 w0, w1;
+        w0.x = pack_bf16x2(o[0], o[1]); w0.y = pack_bf16x2(o[2], o[3]); w0.z = pack_bf16x2(o[4], o[5]); w0.w = pack_bf16x2(o[6], o[7]);
+        w1.x = pack_bf16x2(o[8], o[9]); w1.y = pack_bf16x2(o[10], o[11]); w1.z = pack_bf16x2(o[12], o[13]); w1.w = pack_bf16x2(o[14], o[15]);
+        reinterpret_cast<uint4*>(crow)[0] = w0;
+        reinterpret_cast<uint4*>(crow)[1] = w1;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (on0 + j < nout) crow[j] = f2bf(o[j]);
+      }
+      return;
+    }
+    if (p.epilogue != VSB_EPI_NONE) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.epilogue);
+    }
+    const bool full = (n0 + 32 <= p.N);
+    if (p.out_fp32) {
+      float* crow = reinterpret_cast<float*>(p.C) + orow * p.ldc + n0;
+      const float* rrow = p.residual ? reinterpret_cast<const float*>(p.residual) + orow * p.ldr + n0 : nullptr;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (full || n0 + j < p.N) {
+          float x = f[j];
+          if (rrow) x += rrow[j];
+          crow[j] = x;
+        }
+      }
+    } else {
+      bf16* crow = reinterpret_cast<bf16*>(p.C) + orow * p.ldc + n0;
+      const bf16* rrow = p.residual ? reinterpret_cast<const bf16*>(p.residual) + orow * p.ldr + n0 : nullptr;
+      const bool vec_ok = full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) &&
+                          (rrow == nullptr || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
+      if (vec_ok) {
+        if (rrow) {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            uint4 r = reinterpret_cast<const uint4*>(rrow)[j4];
+            float2 t;
+            t = unpack_bf16x2(r.x); f[j4 * 8 + 0] += t.x; f[j4 * 8 + 1] += t.y;
+            t = unpack_bf16x2(r.y); f[j4 * 8 + 2] += t.x; f[j4 * 8 + 3] += t.y;
+            t = unpack_bf16x2(r.z); f[j4 * 8 + 4] += t.x; f[j4 * 8 + 5] += t.y;
+            t = unpack_bf16x2(r.w); f[j4 * 8 + 6] += t.x; f[j4 * 8 + 7] += t.y;
+          }
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          uint4 w;
+          w.x = pack_bf16x2(f[j4 * 8 + 0], f[j4 * 8 + 1]);
+          w.y = pack_bf16x2(f[j4 * 8 + 2], f[j4 * 8 + 3]);
+          w.z = pack_bf16x2(f[j4 * 8 + 4], f[j4 * 8 + 5]);
+          w.w = pack_bf16x2(f[j4 * 8 + 6], f[j4 * 8 + 7]);
+          reinterpret_cast<uint4*>(crow)[j4] = w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (full || n0 + j < p.N) {
+            float x = f[j];
+            if (rrow) x += bf2f(rrow[j]);
+            crow[j] = f2bf(x);
+          }
+        }
+      }
+    }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(256, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -207,8 +320,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % p.tiles_m;
-        const int n_blk = tile / p.tiles_m;
+        int m_blk, n_blk;
+        tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, m_blk, n_blk);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
@@ -257,8 +370,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     int it = 0;
     const bool swiglu = (p.epilogue == VSB_EPI_SWIGLU);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile % p.tiles_m;
-      const int n_blk = tile / p.tiles_m;
+      int m_blk, n_blk;
+      tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, m_blk, n_blk);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -275,101 +388,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         tmem_ld_wait();
         const int n0 = n_blk * BN + c * 32;
         if (!row_ok || n0 >= p.N) continue;
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
-          if (n0 + 32 <= p.N) {
-            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              uint4 b = __ldg(bp + j4);
-              float2 t;
-              t = unpack_bf16x2(b.x); f[j4 * 8 + 0] += t.x; f[j4 * 8 + 1] += t.y;
-              t = unpack_bf16x2(b.y); f[j4 * 8 + 2] += t.x; f[j4 * 8 + 3] += t.y;
-              t = unpack_bf16x2(b.z); f[j4 * 8 + 4] += t.x; f[j4 * 8 + 5] += t.y;
-              t = unpack_bf16x2(b.w); f[j4 * 8 + 6] += t.x; f[j4 * 8 + 7] += t.y;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) f[j] += bf2f(p.bias[n0 + j]);
-          }
-        }
-        if (swiglu) {
-          // interleaved weight rows: even column = gate_j, odd column = up_j -> out column (n0/2 + j)
-          const int on0 = n0 >> 1;
-          const int nout = p.N >> 1;
-          float o[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = silu_f(f[2 * j]) * f[2 * j + 1];
-          bf16* crow = reinterpret_cast<bf16*>(p.C) + orow * p.ldc + on0;
-          if (on0 + 16 <= nout && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
-            uint4 w0, w1;
-            w0.x = pack_bf16x2(o[0], o[1]); w0.y = pack_bf16x2(o[2], o[3]); w0.z = pack_bf16x2(o[4], o[5]); w0.w = pack_bf16x2(o[6], o[7]);
-            w1.x = pack_bf16x2(o[8], o[9]); w1.y = pack_bf16x2(o[10], o[11]); w1.z = pack_bf16x2(o[12], o[13]); w1.w = pack_bf16x2(o[14], o[15]);
-            reinterpret_cast<uint4*>(crow)[0] = w0;
-            reinterpret_cast<uint4*>(crow)[1] = w1;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (on0 + j < nout) crow[j] = f2bf(o[j]);
-          }
-          continue;
-        }
-        if (p.epilogue != VSB_EPI_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.epilogue);
-        }
-        const bool full = (n0 + 32 <= p.N);
-        if (p.out_fp32) {
-          float* crow = reinterpret_cast<float*>(p.C) + orow * p.ldc + n0;
-          const float* rrow = p.residual ? reinterpret_cast<const float*>(p.residual) + orow * p.ldr + n0 : nullptr;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (full || n0 + j < p.N) {
-              float x = f[j];
-              if (rrow) x += rrow[j];
-              crow[j] = x;
-            }
-          }
-        } else {
-          bf16* crow = reinterpret_cast<bf16*>(p.C) + orow * p.ldc + n0;
-          const bf16* rrow = p.residual ? reinterpret_cast<const bf16*>(p.residual) + orow * p.ldr + n0 : nullptr;
-          const bool vec_ok = full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) &&
-                              (rrow == nullptr || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
-          if (vec_ok) {
-            if (rrow) {
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                uint4 r = reinterpret_cast<const uint4*>(rrow)[j4];
-                float2 t;
-                t = unpack_bf16x2(r.x); f[j4 * 8 + 0] += t.x; f[j4 * 8 + 1] += t.y;
-                t = unpack_bf16x2(r.y); f[j4 * 8 + 2] += t.x; f[j4 * 8 + 3] += t.y;
-                t = unpack_bf16x2(r.z); f[j4 * 8 + 4] += t.x; f[j4 * 8 + 5] += t.y;
-                t = unpack_bf16x2(r.w); f[j4 * 8 + 6] += t.x; f[j4 * 8 + 7] += t.y;
-              }
-            }
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              uint4 w;
-              w.x = pack_bf16x2(f[j4 * 8 + 0], f[j4 * 8 + 1]);
-              w.y = pack_bf16x2(f[j4 * 8 + 2], f[j4 * 8 + 3]);
-              w.z = pack_bf16x2(f[j4 * 8 + 4], f[j4 * 8 + 5]);
-              w.w = pack_bf16x2(f[j4 * 8 + 6], f[j4 * 8 + 7]);
-              reinterpret_cast<uint4*>(crow)[j4] = w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (full || n0 + j < p.N) {
-                float x = f[j];
-                if (rrow) x += bf2f(rrow[j]);
-                crow[j] = f2bf(x);
-              }
-            }
-          }
-        }
+        epilogue_store(p, v, orow, n0, swiglu);
       }
       // release this accumulator buffer to the MMA warp
       tc_fence_before();
@@ -383,6 +402,215 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+
+// ---------------------------------------------------------------- 2-CTA (cta_group::2) variant
+// A CTA pair (cluster 2x1x1, two SMs of one TPC) computes a 256 x 256 tile: CTA r owns A rows / D rows
+// [m0 + 128 r, +128) and HALF of the B tile (W rows [n0 + 128 r, +128)); one `tcgen05.mma.cta_group::2` issued by the
+// leader CTA multiplies the 256-row A (both CTAs' smem) with the 256-row B (both halves).  Per CTA and k-block only
+// (128 + 128) x 64 bf16 = 32 KB come from L2 instead of (128 + 256) x 64: -33 % L2->SM traffic, which is what bounds the
+// single-CTA kernel on the big 7B shapes.  Synchronisation follows the CUTLASS sm100 2SM pipelines:
+//   * both CTAs' TMA loads complete_tx on the LEADER's full barrier (cta_group::2 TMA, peer bit of the mbarrier address
+//     cleared); the leader's producer arms it with the bytes of both CTAs;
+//   * the leader's tcgen05.commit multicasts to the empty barriers (and to the accumulator-full barriers) of both CTAs;
+//   * the epilogue warps of both CTAs arrive on the LEADER's accumulator-empty barrier (remote mbarrier arrive).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // cute::Sm100MmaPeerBitMask: shared::cluster address of the pair's even CTA
+
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit -> arrive on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm_mcast(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+
+struct Smem2 {
+  static constexpr int A_BYTES = BM * BK * 2;          // 128 rows of A
+  static constexpr int B_BYTES = 128 * BK * 2;         // this CTA's half of the 256-row B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using L = Smem2;
+  constexpr int STAGES = L::STAGES;
+  constexpr int BN2 = 256;                 // cluster tile N (and accumulator columns per CTA)
+  constexpr uint32_t TMEM_COLS = 512;      // 2 accumulator buffers x 256 columns
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_tiles = p.tiles_m * p.tiles_n;       // cluster tiles (256 x 256)
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);       // leader's producer arrive (+ tx bytes of both CTAs); unused in the peer
+      mbar_init(&empty_bar[s], 1);      // one multicast commit from the leader's MMA thread
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);      // one multicast commit
+      mbar_init(&tempty_bar[a], 8);     // 4 epilogue warps x 2 CTAs (leader's copy is the one used)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_ptr_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                   // peer barriers initialised + both TMEM allocations done
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        int m_blk, n_blk;
+        tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, m_blk, n_blk);
+        const int row_a = m_blk * 256 + (int)rank * 128;
+        const int row_b = n_blk * BN2 + (int)rank * 128;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+          tma_load_2d_2sm(sa, &tmA, kb * BK, row_a, &full_bar[stage]);
+          tma_load_2d_2sm(sb, &tmB, kb * BK, row_b, &full_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(256, BN2);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+          const uint64_t da = make_smem_desc(sa);
+          const uint64_t db = make_smem_desc(sb);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_f16_2sm(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm_mcast(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm_mcast(&tfull_bar[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows x 256 columns) =====================
+    const int q = warp & 3;
+    int it = 0;
+    const bool swiglu = (p.epilogue == VSB_EPI_SWIGLU);
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      int m_blk, n_blk;
+      tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, m_blk, n_blk);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int m = m_blk * 256 + (int)rank * 128 + q * 32 + lane;
+      const bool row_ok = m < p.M;
+      long long orow = 0;
+      if (row_ok) orow = (long long)(m / p.rows_per_group) * p.group_stride + p.group_offset + (m % p.rows_per_group);
+#pragma unroll 1
+      for (int c = 0; c < BN2 / 32; ++c) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN2 + c * 32);
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        const int n0 = n_blk * BN2 + c * 32;
+        if (!row_ok || n0 >= p.N) continue;
+        epilogue_store(p, v, orow, n0, swiglu);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);     // leader's accumulator-empty barrier
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();       // nobody leaves (or frees TMEM) while the pair may still touch its smem / barriers / TMEM
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
   }
 }
 
@@ -477,14 +705,36 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, i
   return VSB_OK;
 }
 
-int g_force_bn = 0;
+int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int max_ctas, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VSB_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::TOTAL));
+    attr_set = true;
+  }
+  p.tiles_m = (p.M + 255) / 256;
+  p.tiles_n = (p.N + 255) / 256;
+  const int tiles = p.tiles_m * p.tiles_n;
+  int clusters = max_ctas / 2;
+  if (clusters > tiles) clusters = tiles;
+  if (clusters < 1) clusters = 1;
+  gemm_bf16_tcgen05_2cta_kernel<<<2 * clusters, 256, Smem2::TOTAL, stream>>>(tmA, tmB, p);
+  VSB_LAUNCH_CHECK();
+  return VSB_OK;
+}
+
+int g_force_bn = 0;      // 64/128/256 = single-CTA tile width; 512 = force the 2-CTA 256x256 kernel; 0 = auto
 int g_max_ctas = 0;
+int g_group_m = 0;
 
 }  // namespace
 
 extern "C" int vsb_gemm_set_tuning(int force_bn, int max_ctas) {
   g_force_bn = force_bn;
   g_max_ctas = max_ctas;
+  return VSB_OK;
+}
+extern "C" int vsb_gemm_set_group_m(int group_m) {
+  g_group_m = group_m;
   return VSB_OK;
 }
 
@@ -537,9 +787,25 @@ extern "C" int vsb_gemm_bf16(const void* A, long long lda, const void* W, long l
       if (best < 0 || cost < best) { best = cost; bn = c; }
     }
   }
+  p.group_m = g_group_m > 0 ? g_group_m : 16;
   CUtensorMap tmA, tmB;
   int r = make_tensor_map(&tmA, A, M, K, lda, BM);
   if (r) return r;
+  // 2-CTA 256x256 cluster tiles: chosen when the problem fills the machine with them (less L2->SM traffic per flop)
+  bool use_2cta = (g_force_bn == 512);
+  if (g_force_bn == 0 && M >= 512 && N >= 512) {
+    const long long t2 = (long long)((M + 255) / 256) * ((N + 255) / 256);
+    const long long waves2 = (t2 + sms / 2 - 1) / (sms / 2);
+    const double eff2 = (double)t2 / (double)(waves2 * (sms / 2));      // wave-quantisation efficiency of the 256x256 tiling
+    const double fill = ((double)M * N) / ((double)((M + 255) / 256 * 256) * ((N + 255) / 256 * 256));
+    use_2cta = eff2 * fill >= 0.80;
+  }
+  if (use_2cta) {
+    p.group_m = g_group_m > 0 ? g_group_m : 8;
+    r = make_tensor_map(&tmB, W, N, K, ldw, 128);
+    if (r) return r;
+    return launch_gemm_2cta(tmA, tmB, p, sms, stream);
+  }
   r = make_tensor_map(&tmB, W, N, K, ldw, bn);
   if (r) return r;
   if (bn == 256) return launch_gemm<256>(tmA, tmB, p, sms, stream);

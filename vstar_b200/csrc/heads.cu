@@ -172,36 +172,54 @@ __global__ void __launch_bounds__(256) stats_final_kernel(const float* __restric
 
 // ---------------------------------------------------------------- rectangle sums of the normalised heatmap
 // out[r] = sum over rect r of  (hm[y,x] - sub) * mul     (normalize_score folded in: sub = min, mul = 1/(max-min), or 0/0)
-//   (/root/reference/visual_search.py:255-275).  One block per rectangle, fp32 per-thread partials, fp64 block combine.
-__global__ void __launch_bounds__(256) rect_sums_kernel(const float* __restrict__ hm, int h, int w, const int* __restrict__ rects,
-                                                        int nrects, const float* __restrict__ stats, double* __restrict__ out) {
+//   (/root/reference/visual_search.py:255-275).  grid = (RECT_CHUNKS, nrects): every block reduces a band of rows of its
+// rectangle (coalesced row segments, fp32 per-thread partials flushed to fp64 every 64 elements), then a tiny second kernel
+// combines the RECT_CHUNKS partials per rectangle in a fixed order (deterministic).
+constexpr int RECT_CHUNKS = 64;
+
+__global__ void __launch_bounds__(256) rect_sums_partial_kernel(const float* __restrict__ hm, int h, int w, const int* __restrict__ rects,
+                                                                const float* __restrict__ stats, double* __restrict__ partial) {
   __shared__ double red[8];
-  const int r = blockIdx.x;
-  if (r >= nrects) return;
+  const int r = blockIdx.y, chunk = blockIdx.x;
   int x0 = rects[r * 4 + 0], y0 = rects[r * 4 + 1], rw = rects[r * 4 + 2], rh = rects[r * 4 + 3];
   int x1 = x0 + rw, y1 = y0 + rh;
   if (x0 < 0) x0 = 0; if (y0 < 0) y0 = 0; if (x1 > w) x1 = w; if (y1 > h) y1 = h;
   const float mx = stats[0], mn = stats[1];
   const float mul = (mx != mn) ? 1.f / (mx - mn) : 0.f;
   const float sub = (mx != mn) ? mn : 0.f;
-  const long long cnt = (x1 > x0 && y1 > y0) ? (long long)(x1 - x0) * (y1 - y0) : 0;
-  const int cw = x1 - x0;
-  float acc = 0.f;
   double dacc = 0.0;
-  int k = 0;
-  for (long long i = threadIdx.x; i < cnt; i += blockDim.x) {
-    const int yy = y0 + i / cw, xx = x0 + i % cw;
-    acc += (hm[(long long)yy * w + xx] - sub) * mul;
-    if (++k == 256) { dacc += acc; acc = 0.f; k = 0; }
+  if (x1 > x0 && y1 > y0) {
+    const int rows = y1 - y0;
+    const int per = (rows + RECT_CHUNKS - 1) / RECT_CHUNKS;
+    const int ya = y0 + chunk * per;
+    const int yb = min(y1, ya + per);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int yy = ya + warp; yy < yb; yy += 8) {           // one warp per row: coalesced
+      const float* row = hm + (long long)yy * w;
+      float acc = 0.f;
+      int k = 0;
+      for (int xx = x0 + lane; xx < x1; xx += 32) {
+        acc += (row[xx] - sub) * mul;
+        if (++k == 64) { dacc += acc; acc = 0.f; k = 0; }
+      }
+      dacc += acc;
+    }
   }
-  dacc += acc;
   for (int o = 16; o > 0; o >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dacc;
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int q = 1; q < 8; ++q) dacc += red[q];
-    out[r] = dacc;
+    partial[(long long)r * RECT_CHUNKS + chunk] = dacc;
   }
+}
+
+__global__ void rect_sums_final_kernel(const double* __restrict__ partial, int nrects, double* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrects) return;
+  double s = 0.0;
+  for (int c = 0; c < RECT_CHUNKS; ++c) s += partial[(long long)r * RECT_CHUNKS + c];
+  out[r] = s;
 }
 
 // strided 2-D copy of 16-byte vectors: dst[r, :] = src[r, :]
@@ -287,10 +305,13 @@ extern "C" int vsb_heatmap_bilinear_f32(const void* low, int LH, int LW, void* o
 }
 
 extern "C" int vsb_rect_sums_f32(const void* hm, int h, int w, const void* rects, int nrects, const void* stats3, void* out_f64,
-                                 void* stream) {
-  VSB_CHECK_ARG(hm && rects && stats3 && out_f64, "vsb_rect_sums_f32: null pointer");
+                                 void* scratch_f64, void* stream) {
+  VSB_CHECK_ARG(hm && rects && stats3 && out_f64 && scratch_f64, "vsb_rect_sums_f32: null pointer (scratch = 64*nrects doubles)");
   if (nrects <= 0) return VSB_OK;
-  rect_sums_kernel<<<nrects, 256, 0, STREAM(stream)>>>((const float*)hm, h, w, (const int*)rects, nrects, (const float*)stats3, (double*)out_f64);
+  dim3 grid(RECT_CHUNKS, nrects);
+  rect_sums_partial_kernel<<<grid, 256, 0, STREAM(stream)>>>((const float*)hm, h, w, (const int*)rects, (const float*)stats3, (double*)scratch_f64);
+  VSB_LAUNCH_CHECK();
+  rect_sums_final_kernel<<<(nrects + 63) / 64, 64, 0, STREAM(stream)>>>((const double*)scratch_f64, nrects, (double*)out_f64);
   VSB_LAUNCH_CHECK();
   return VSB_OK;
 }

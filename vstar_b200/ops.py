@@ -302,7 +302,10 @@ def heatmap(low, h, w, clamp=True, with_stats=True, out=None):
 def rect_sums(hm, rects, stats):
     """hm [h,w] fp32, rects int32 [n,4] (x,y,w,h), stats [3] -> float64 [n] sums of the normalised map"""
     assert rects.dtype == torch.int32 and rects.is_contiguous()
-    out = torch.empty((rects.shape[0],), dtype=torch.float64, device=hm.device)
-    _lib.launches += 1
-    call("vsb_rect_sums_f32", hm.data_ptr(), hm.shape[0], hm.shape[1], rects.data_ptr(), rects.shape[0], stats.data_ptr(), out.data_ptr(), _stream())
+    n = rects.shape[0]
+    out = torch.empty((n,), dtype=torch.float64, device=hm.device)
+    scratch = torch.empty((64 * n,), dtype=torch.float64, device=hm.device)
+    _lib.launches += 2
+    call("vsb_rect_sums_f32", hm.data_ptr(), hm.shape[0], hm.shape[1], rects.data_ptr(), n, stats.data_ptr(), out.data_ptr(),
+         scratch.data_ptr(), _stream())
     return out
