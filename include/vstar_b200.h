@@ -78,6 +78,8 @@ int vsb_copy2d_b16(const void* src, long long lds, void* dst, long long ldd, lon
 int vsb_flash_attn_bf16(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_rs, long long k_bs,
                         long long k_rs, long long v_bs, long long v_rs, long long o_bs, long long o_rs, int B, int H, int Sq, int Sk,
                         int D, int causal, float scale, void* stream);
+/* testing hook: 0 = auto (tcgen05 kernel for Sq >= 64, mma.sync kernel for decode-sized Sq), 1 = mma.sync, 2 = tcgen05 */
+int vsb_attn_set_impl(int impl);
 /* SAM two-way transformer attention, head_dim 16/32 (segment_anything/modeling/transformer.py:220-242). */
 int vsb_attn_small_bf16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
                         int B, int H, int Nq, int Nk, int D, float scale, void* stream);

@@ -210,11 +210,20 @@ def test_rope_bit_exact(ops):
     assert torch.equal(out2[:, :, 2], qkv.view(B, T, 3, H, D)[:, :, 2])
 
 
+@pytest.mark.parametrize("impl", [1, 2])
 @pytest.mark.parametrize("B,H,S,D,causal", [(1, 2, 257, 64, False), (2, 3, 2305, 64, False), (2, 4, 320, 128, True),
-                                            (1, 2, 64, 128, True), (3, 2, 1, 128, False), (1, 1, 130, 64, True)])
-def test_flash_attn(ops, B, H, S, D, causal):
+                                            (1, 2, 64, 128, True), (3, 2, 1, 128, False), (1, 1, 130, 64, True),
+                                            (2, 2, 128, 64, False), (1, 3, 384, 128, False), (2, 2, 515, 64, True)])
+def test_flash_attn(ops, B, H, S, D, causal, impl):
+    """impl 1 = mma.sync kernel, 2 = tcgen05 kernel (both behind vsb_flash_attn_bf16)"""
+    from vstar_b200 import _lib
     qkv = rnd(B * S, 3 * H * D, seed=40)
-    out = ops.attn_fused_qkv(qkv, B, S, H, D, causal, D ** -0.5)
+    _lib.call("vsb_attn_set_impl", impl)
+    try:
+        out = ops.attn_fused_qkv(qkv, B, S, H, D, causal, D ** -0.5)
+        torch.cuda.synchronize()
+    finally:
+        _lib.call("vsb_attn_set_impl", 0)
     q, k, v = [t.transpose(1, 2).float() for t in qkv.view(B, S, 3, H, D).unbind(2)]
     att = q @ k.transpose(-1, -2) * D ** -0.5
     if causal:
@@ -223,14 +232,24 @@ def test_flash_attn(ops, B, H, S, D, causal):
     assert torch.allclose(out.float(), ref, rtol=2e-2, atol=2e-2), rel_err(out, ref)
 
 
-def test_flash_attn_kv_cache_decode(ops):
-    """Sq < Sk with causal offset (decode step against a KV cache with a different row stride)"""
-    B, H, D, Sk, Sq, Tmax = 2, 4, 128, 100, 3, 128
+@pytest.mark.parametrize("impl,Sq,Sk", [(1, 3, 100), (2, 3, 100), (2, 70, 300), (1, 70, 300)])
+def test_flash_attn_kv_cache_decode(ops, impl, Sq, Sk):
+    """Sq < Sk with causal offset (decode / chunked prefill against a KV cache with a different row stride; cache rows
+    beyond Sk hold NaNs and must never be read into the result)"""
+    from vstar_b200 import _lib
+    B, H, D, Tmax = 2, 4, 128, 384
     q = rnd(B * Sq, H * D, seed=41)
     kc, vc = rnd(B, Tmax, H * D, seed=42), rnd(B, Tmax, H * D, seed=43)
+    kc[:, Sk:] = float("nan")
+    vc[:, Sk:] = float("nan")
     out = torch.empty(B * Sq, H * D, dtype=BF, device="cuda")
-    ops.flash_attn(q, kc, vc, out, B, H, Sq, Sk, D, True, D ** -0.5, Sq * H * D, H * D, Tmax * H * D, H * D, Tmax * H * D, H * D,
-                   Sq * H * D, H * D)
+    _lib.call("vsb_attn_set_impl", impl)
+    try:
+        ops.flash_attn(q, kc, vc, out, B, H, Sq, Sk, D, True, D ** -0.5, Sq * H * D, H * D, Tmax * H * D, H * D, Tmax * H * D, H * D,
+                       Sq * H * D, H * D)
+        torch.cuda.synchronize()
+    finally:
+        _lib.call("vsb_attn_set_impl", 0)
     qf = q.view(B, Sq, H, D).transpose(1, 2).float()
     kf = kc[:, :Sk].view(B, Sk, H, D).transpose(1, 2).float()
     vf = vc[:, :Sk].view(B, Sk, H, D).transpose(1, 2).float()

@@ -50,12 +50,18 @@ def main():
         res.append(dict(kernel="gemm", name=name, M=M, N=N, K=K, ms=ms, tflops=tf, torch_ms=ms_t, torch_tflops=2 * M * N * K / ms_t / 1e9, variants=var))
         print(res[-1], flush=True)
     for B, H, S, D, causal, name in [(8, 32, 320, 128, True, "llama prefill B=8"), (8, 12, 2305, 64, False, "owl B=8"),
-                                     (8, 16, 257, 64, False, "clip B=8"), (64, 32, 320, 128, True, "llama prefill B=64")]:
+                                     (8, 16, 257, 64, False, "clip B=8"), (64, 32, 320, 128, True, "llama prefill B=64"),
+                                     (32, 12, 2305, 64, False, "owl B=32")]:
         qkv = torch.randn(B * S, 3 * H * D, device="cuda").to(BF)
         out = torch.empty(B * S, H * D, dtype=BF, device="cuda")
-        ms = timeit(lambda: ops.attn_fused_qkv(qkv, B, S, H, D, causal, D ** -0.5, out=out))
         fl = 4 * B * H * S * S * D * (0.5 if causal else 1.0)
-        res.append(dict(kernel="flash_attn", name=name, ms=ms, tflops=fl / ms / 1e9))
+        var = {}
+        for tag, impl in (("mma_sync", 1), ("tcgen05", 2)):
+            _lib.call("vsb_attn_set_impl", impl)
+            var[tag] = round(fl / timeit(lambda: ops.attn_fused_qkv(qkv, B, S, H, D, causal, D ** -0.5, out=out)) / 1e9, 1)
+        _lib.call("vsb_attn_set_impl", 0)
+        ms = timeit(lambda: ops.attn_fused_qkv(qkv, B, S, H, D, causal, D ** -0.5, out=out))
+        res.append(dict(kernel="flash_attn", name=name, ms=ms, tflops=fl / ms / 1e9, variants=var))
         print(res[-1], flush=True)
     for rows, cols in [(2560, 4096), (18440, 768)]:
         x = torch.randn(rows, cols, device="cuda").to(BF)

@@ -32,6 +32,7 @@ SIGNATURES = {
     "vsb_argmax_rows_f32": [c_p, c_ll, c_i, c_i, c_p, c_p, c_p],
     "vsb_copy2d_b16": [c_p, c_ll, c_p, c_ll, c_ll, c_i, c_p],
     "vsb_flash_attn_bf16": [c_p, c_p, c_p, c_p, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
+    "vsb_attn_set_impl": [c_i],
     "vsb_attn_small_bf16": [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
     "vsb_owl_class_post": [c_p, c_ll, c_p, c_ll, c_i, c_ll, c_i, c_p, c_p, c_p],
     "vsb_owl_box_post": [c_p, c_ll, c_p, c_i, c_ll, c_p, c_p],

@@ -314,6 +314,13 @@ __global__ void __launch_bounds__(128) attn_small_kernel(const bf16* __restrict_
 
 }  // namespace
 
+// tcgen05 kernel (attention_tc.cu)
+int vsb_flash_attn_tc(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_rs, long long k_bs, long long k_rs,
+                      long long v_bs, long long v_rs, long long o_bs, long long o_rs, int B, int H, int Sq, int Sk, int D, int causal,
+                      float scale, cudaStream_t stream);
+static int g_attn_impl = 0;   // 0 auto, 1 = mma.sync kernel, 2 = tcgen05 kernel
+extern "C" int vsb_attn_set_impl(int impl) { g_attn_impl = impl; return VSB_OK; }
+
 extern "C" int vsb_flash_attn_bf16(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_rs,
                                    long long k_bs, long long k_rs, long long v_bs, long long v_rs, long long o_bs,
                                    long long o_rs, int B, int H, int Sq, int Sk, int D, int causal, float scale, void* stream) {
@@ -325,6 +332,9 @@ extern "C" int vsb_flash_attn_bf16(const void* q, const void* k, const void* v, 
                 "vsb_flash_attn_bf16: strides must be multiples of 8 elements (16 B)");
   VSB_CHECK_ARG(((uintptr_t)q & 15) == 0 && ((uintptr_t)k & 15) == 0 && ((uintptr_t)v & 15) == 0 && ((uintptr_t)o & 15) == 0,
                 "vsb_flash_attn_bf16: pointers must be 16-byte aligned");
+  if (g_attn_impl == 2 || (g_attn_impl == 0 && Sq >= 64))
+    return vsb_flash_attn_tc(q, k, v, o, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, B, H, Sq, Sk, D, causal, scale,
+                             reinterpret_cast<cudaStream_t>(stream));
   AttnParams p;
   p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v; p.o = (bf16*)o;
   p.q_bs = q_bs; p.q_rs = q_rs; p.k_bs = k_bs; p.k_rs = k_rs; p.v_bs = v_bs; p.v_rs = v_rs; p.o_bs = o_bs; p.o_rs = o_rs;
