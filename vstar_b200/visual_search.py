@@ -258,8 +258,8 @@ class SearchController:
         self.scorer = scorer if scorer is not None else CudaScorer()
         self.batch_size = max(1, int(batch_size))
         self.extract_noun_chunks = extract_noun_chunks
-        self.batched = hasattr(vsm, "detect_batch")
         self.regions = hasattr(vsm, "detect_regions")
+        self.batched = self.regions or hasattr(vsm, "detect_batch")
 
     # -- evaluation ----------------------------------------------------------------------------------------
     def _evaluate(self, requests):
