@@ -71,6 +71,9 @@ int vsb_owl_merge_bf16(const void* x, const void* w1, const void* b1, const void
 int vsb_add_rows_bf16(const void* a, const void* b, void* y, long long rows, int cols, long long bmod, void* stream);
 int vsb_cast_f32_bf16(const void* x, void* y, long long n, void* stream);
 int vsb_argmax_rows_f32(const void* x, long long ld, int rows, int n, void* idx_i32, void* val_f32, void* stream);
+/* per-row negative log-likelihood of labels under softmax(logits) — option scoring of the SEAL VQA LLM
+ * (CrossEntropyLoss, /root/reference/vstar_bench_eval.py:154-159) */
+int vsb_nll_rows_f32(const void* logits, long long ld, int rows, int n, const void* labels_i64, void* out_f32, void* stream);
 int vsb_copy2d_b16(const void* src, long long lds, void* dst, long long ldd, long long rows, int cols, void* stream);
 
 /* softmax(QK^T*scale [+causal]) V, head_dim 64/128; element (b,s,h,d) at base + b*bs + s*rs + h*D + d.
@@ -80,7 +83,8 @@ int vsb_flash_attn_bf16(const void* q, const void* k, const void* v, void* o, lo
                         int D, int causal, float scale, void* stream);
 /* testing hook: 0 = auto (tcgen05 kernel for Sq >= 64, mma.sync kernel for decode-sized Sq), 1 = mma.sync, 2 = tcgen05 */
 int vsb_attn_set_impl(int impl);
-/* SAM two-way transformer attention, head_dim 16/32 (segment_anything/modeling/transformer.py:220-242). */
+/* SAM two-way transformer attention, head_dim 16/32 (segment_anything/modeling/transformer.py:220-242)
+ * and SEAL perceiver-resampler attention, head_dim 96 (LLaVA/llava/model/multimodal_projector/perceiver.py:25-77). */
 int vsb_attn_small_bf16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
                         int B, int H, int Nq, int Nk, int D, float scale, void* stream);
 

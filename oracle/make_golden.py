@@ -282,6 +282,82 @@ def case_search_model(m, sd, cfg, tag, img_seed, w, h, smallest, **kw):
     print(f"   path_length={pl}, success={ok}, nodes={len(path2)}")
 
 
+def build_reference_vqa_model(cfg, sd):
+    owl, clip = hf_cfgs(cfg)
+    ref_shims.install(owl, clip)
+    from LLaVA.llava.model.language_model.llava_search_llama import LlavaSearchLlamaForCausalLM, LlavaSearchConfig
+    lc = LlavaSearchConfig(hidden_size=cfg.hidden, intermediate_size=cfg.intermediate, num_hidden_layers=cfg.n_layers,
+                           num_attention_heads=cfg.n_heads, num_key_value_heads=cfg.n_heads, vocab_size=cfg.vocab,
+                           rms_norm_eps=cfg.rms_eps, max_position_embeddings=2048, mm_vision_tower="openai/fake-clip",
+                           mm_hidden_size=cfg.clip_hidden, mm_vision_select_layer=cfg.clip_select_layer,
+                           mm_projector_type="linear", object_mm_projector_type="perceiver", mm_use_im_start_end=False,
+                           attn_implementation="eager")
+    torch.manual_seed(0)
+    m = LlavaSearchLlamaForCausalLM(lc)
+    m.get_model().get_vision_tower().load_model()
+    m.eval()
+    ref_keys = set(m.state_dict().keys())
+    assert all(k in ref_keys for k in sd), [k for k in sd if k not in ref_keys][:5]
+    missing = m.load_state_dict(sd, strict=False)
+    assert not [k for k in missing.missing_keys if "post_layernorm" not in k and "position_ids" not in k], missing.missing_keys[:5]
+    return m
+
+
+def case_vqa(tag, img_seed):
+    """SEAL VQA-LLM forward (image short + 2 object crops long, the k<=2 configuration of vstar_bench_eval.py:231-236),
+    option scoring and a short greedy generation, from the REAL reference LlavaSearchLlamaForCausalLM."""
+    from oracle import vqa_oracle as V
+    from vstar_b200 import synth
+    print(f"[golden] vqa case {tag}")
+    cfg = O.tiny_config()
+    shapes = V.vqa_state_dict_shapes(cfg)
+    sd = {k: synth.synthetic_tensor(k, shp, seed=4321) for k, shp in shapes.items()}
+    m = build_reference_vqa_model(cfg, sd)
+    g = torch.Generator().manual_seed(img_seed)
+    image = torch.randn(1, 3, 224, 224, generator=g)
+    crops = torch.randn(2, 3, 224, 224, generator=g)
+    hi = cfg.vocab - 24
+    q = torch.randint(3, hi, (1, 30), generator=g)
+    q[0, 0] = 1
+    q[0, 6] = -200
+    q[0, 20] = -300
+    q[0, 24] = -300
+    opts = [torch.randint(3, hi, (n,), generator=g) for n in (3, 5, 4, 2)]
+    for images_long, objects_long, sub in (([False], [True, True], "short_long"), ([True], [False, False], "long_short")):
+        with torch.no_grad():
+            ref = m(q, images=image, object_features=crops, images_long=images_long, objects_long=objects_long).logits
+        emb = V.build_embeds(sd, cfg, q, image, crops, images_long, objects_long)
+        orc = V.forward_logits(sd, cfg, emb)
+        close(orc, ref, f"vqa logits {sub}", atol=1e-4)
+        # option losses through full teacher-forced forwards of the reference (== its shared-prefix KV reuse)
+        ref_losses = []
+        for o in opts:
+            full = torch.cat([q, o.unsqueeze(0)], dim=1)
+            with torch.no_grad():
+                lg = m(full, images=image, object_features=crops, images_long=images_long, objects_long=objects_long).logits
+            Tq = ref.shape[1]
+            ref_losses.append(torch.nn.functional.cross_entropy(lg[0, Tq - 1:Tq - 1 + o.numel()], o))
+        ref_losses = torch.stack(ref_losses)
+        o_losses, o_choice = V.option_losses(sd, cfg, q, opts, image, crops, images_long, objects_long)
+        close(o_losses, ref_losses, f"option NLL {sub}", atol=1e-4)
+        assert o_choice == int(ref_losses.argmin())
+        # greedy generation around the reference forward
+        ids = q.clone()
+        gen = []
+        for _ in range(4):
+            with torch.no_grad():
+                lg = m(ids, images=image, object_features=crops, images_long=images_long, objects_long=objects_long).logits
+            t = int(lg[0, -1].argmax())
+            gen.append(t)
+            ids = torch.cat([ids, torch.tensor([[t]])], dim=1)
+        assert V.free_form_generate(sd, cfg, q, image, crops, images_long, objects_long, max_new_tokens=4, eos_token_id=-1) == gen
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"vqa_{tag}_{sub}.npz"), img_seed=img_seed, q=q.numpy(),
+                            opts=np.concatenate([o.numpy() for o in opts]), opt_lens=np.array([o.numel() for o in opts]),
+                            images_long=np.array(images_long), objects_long=np.array(objects_long),
+                            logits_last=ref[0, -1].numpy(), logits_argmax=ref[0].argmax(-1).numpy(), T=ref.shape[1],
+                            option_losses=ref_losses.numpy(), gen=np.array(gen))
+
+
 def main():
     assert ref_shims.reference_available(), "needs /root/reference (build container only)"
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -300,6 +376,7 @@ def main():
                 target_cue_threshold=50.0, target_cue_threshold_minimum=40.0)
     case_search_model(m, sd, cfg, "a", img_seed=31, w=640, h=512, smallest=200, confidence_high=2.0,
                       target_cue_threshold=-1e9, target_cue_threshold_minimum=-1e9)
+    case_vqa("a", img_seed=41)
     print("golden vectors written to", GOLDEN_DIR)
 
 

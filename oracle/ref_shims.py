@@ -73,6 +73,14 @@ def install(owl_cfg: dict, clip_cfg: dict):
 
     stub("VisualSearch.model.llava.model.language_model.llava_mpt",
          LlavaMPTConfig=_Dummy, LlavaMPTForCausalLM=_Dummy)
+    stub("LLaVA.llava.model.language_model.llava_mpt", LlavaMPTConfig=_Dummy, LlavaMPTForCausalLM=_Dummy)
+    try:
+        import einops_exts  # noqa: F401
+    except Exception:
+        import einops
+        stub("einops_exts",
+             rearrange_many=lambda ts, pattern, **kw: tuple(einops.rearrange(t, pattern, **kw) for t in ts),
+             repeat_many=lambda ts, pattern, **kw: tuple(einops.repeat(t, pattern, **kw) for t in ts))
     if "spacy" not in sys.modules:
         try:
             import spacy  # noqa: F401

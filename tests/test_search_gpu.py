@@ -120,3 +120,27 @@ def test_draft_mismatch_falls_back_to_exact_greedy(tiny_vsm):
         last = logits[0, -1]
         assert float(last.max() - last[t]) < 3e-2, (t, int(last.argmax()), float(last.max() - last[t]))
         ids = torch.cat([ids, torch.tensor([[t]])], dim=1)
+
+
+def test_vsmforcausallm_mirror_api(tiny_vsm):
+    """VSMForCausalLM.inference / .model_forward return conventions of VisualSearch/model/VSM.py:438-553, :201-364"""
+    from vstar_b200.vsm import VSMForCausalLM
+    vsm, O, cfg, sd = tiny_vsm
+    m = VSMForCausalLM(vsm.engine)
+    assert m.get_model().get_vision_tower() is not None and m.eval() is m and m.config.vision_tower
+    img = synth_image(80, 160, 120)
+    prompt, ans = O.synthetic_prompt(cfg, n_text=24, seed=5)
+    ids = torch.cat([prompt, ans.unsqueeze(0)], dim=1)
+    ic, io = O.preprocess_clip(img).cuda(), O.preprocess_owl(img).cuda()
+    out = m.model_forward(images=io, images_clip=ic, input_ids=ids.cuda(), original_size_list=[(120, 160)])
+    assert out["pred_masks"][0].shape == (1, 120, 160) and out["pred_logits"].shape == (1, 2304, 1) and out["pred_boxes"].shape == (1, 2304, 4)
+    ref = O.model_forward_inference(sd, cfg, O.preprocess_owl(img), O.preprocess_clip(img), ids, (120, 160))
+    e = float((out["pred_masks"][0][0].cpu() - ref["pred_masks"][0]).abs().max() / ref["pred_masks"][0].abs().max())
+    assert e < 5e-2, e
+    # generate-based entry point: 'vqa' returns ids only; random weights emit no [LOC] within 6 tokens -> the reference's
+    # "empty pred_masks" outcome (its wrapper then raises IndexError, visual_search.py:209-211)
+    oid, pm, det = m.inference(ic, io, prompt.cuda(), [(768, 768)], [(120, 160)], max_new_tokens=6, mode="vqa")
+    assert oid.shape[0] == 1 and oid.shape[1] > prompt.shape[1] and pm is None and det is None
+    oid2, pm2, det2 = m.inference(ic, io, prompt.cuda(), [(768, 768)], [(120, 160)], max_new_tokens=6, mode="detection")
+    if cfg.loc_token_idx not in oid[0].tolist():
+        assert pm2 == [] and det2 is None

@@ -1,0 +1,108 @@
+"""SEAL VQA LLM on the GPU (vstar_b200/vqa.py) against the goldens produced by the REAL reference
+LlavaSearchLlamaForCausalLM (tests/golden/vqa_*.npz, fp32) and the CPU oracle in bf16.
+Tolerance: the reference runs this model in fp16, the kernels are bf16/fp32-accumulate; we require
+err_new <= 2 * err(bf16 oracle) + 5e-3 on logits, identical option choice when the reference's NLL gap exceeds 0.05,
+identical greedy ids where the reference's top-2 logit gap exceeds 0.05."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from oracle import vqa_oracle as V, vsm_oracle as O
+    from vstar_b200 import synth
+    from vstar_b200.vqa import VQAEngine, VQAWeights
+    cfg = O.tiny_config()
+    sd = {k: synth.synthetic_tensor(k, shp, seed=4321) for k, shp in V.vqa_state_dict_shapes(cfg).items()}
+    eng = VQAEngine(VQAWeights.from_state_dict(cfg, sd), max_tokens=1024)
+    return V, O, cfg, sd, eng
+
+
+def inputs(g):
+    gen = torch.Generator().manual_seed(int(g["img_seed"]))
+    image = torch.randn(1, 3, 224, 224, generator=gen)
+    crops = torch.randn(2, 3, 224, 224, generator=gen)
+    q = torch.from_numpy(g["q"])
+    opts, o = [], 0
+    for n in g["opt_lens"]:
+        opts.append(torch.from_numpy(g["opts"][o:o + int(n)]))
+        o += int(n)
+    return image, crops, q, opts, [bool(x) for x in g["images_long"]], [bool(x) for x in g["objects_long"]]
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).float().cpu(), torch.as_tensor(b).float().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize("sub", ["short_long", "long_short"])
+def test_vqa_forward_options_generate(setup, sub):
+    V, O, cfg, sd, eng = setup
+    g = np.load(os.path.join(G, f"vqa_a_{sub}.npz"))
+    image, crops, q, opts, il, ol = inputs(g)
+    sd_bf = {k: v.to(BF) for k, v in sd.items()}
+    # oracle fp32 == golden (pinned on CPU too); bf16 oracle gives the reference-precision error scale
+    e32 = V.build_embeds(sd, cfg, q, image, crops, il, ol)
+    l32 = V.forward_logits(sd, cfg, e32)
+    assert rel(l32[0, -1], g["logits_last"]) < 1e-4 and l32.shape[1] == int(g["T"])
+    l16 = V.forward_logits(sd_bf, cfg, V.build_embeds(sd_bf, cfg, q, image.to(BF), crops.to(BF), il, ol))
+    e_ref = rel(l16[0], l32[0])
+    ic, cc = image.to(BF).cuda(), crops.to(BF).cuda()
+    x = eng.build_embeds(q[0].tolist(), ic, cc, il, ol)
+    T = x.shape[0]
+    assert T == int(g["T"])
+    eng.prefill_embeds(x)
+    _, am, logits = eng._logits_rows(x, torch.arange(T, device="cuda"))
+    e_new = rel(logits, l32[0])
+    assert e_new <= 2 * e_ref + 5e-3, (e_new, e_ref)
+    top2 = l32[0].topk(2, dim=-1).values
+    confident = (top2[:, 0] - top2[:, 1]) > 0.05
+    assert torch.equal(am.cpu().long()[confident], torch.from_numpy(g["logits_argmax"])[confident])
+    # option scoring with the shared cached prefix
+    losses, choice = eng.option_losses(q[0].tolist(), [o.tolist() for o in opts], ic, cc, il, ol)
+    ref_l = torch.from_numpy(g["option_losses"])
+    assert float((losses - ref_l).abs().max()) < 5e-2, (losses, ref_l)
+    srt = ref_l.sort().values
+    if float(srt[1] - srt[0]) > 0.05:
+        assert choice == int(ref_l.argmin())
+    # greedy generation on the KV cache: every emitted token is (near-)argmax of the fp32 oracle along the emitted path
+    out = eng.generate(q[0].tolist(), ic, cc, il, ol, max_new_tokens=4, eos_token_id=-1)
+    emb = sd["model.embed_tokens.weight"]
+    embeds = e32.clone()
+    for t in out:
+        last = V.forward_logits(sd, cfg, embeds)[0, -1]
+        assert float(last.max() - last[t]) < 3e-2
+        embeds = torch.cat([embeds, emb[torch.tensor([t])].unsqueeze(0)], dim=1)
+    json.dump(dict(err_new=e_new, err_ref_bf16=e_ref, losses=losses.tolist(), ref_losses=ref_l.tolist(), gen=out, ref_gen=g["gen"].tolist()),
+              open(f"gpurun_out/vqa_parity_{sub}.json", "w"))
+
+
+def test_vqa_llm_wrapper_api(setup):
+    """drop-in surface of vstar_bench_eval.VQA_LLM with the synthetic tokenizer"""
+    from PIL import Image
+    from vstar_b200.vqa import VQA_LLM
+    V, O, cfg, sd, eng = setup
+    vqa = VQA_LLM(engine=eng)
+    img = Image.fromarray(np.random.default_rng(3).integers(0, 256, (300, 300, 3), dtype=np.uint8), "RGB")
+    crop = vqa.get_object_crop(img, [50, 60, 40, 30], patch_scale=1.2)
+    assert crop.shape == (3, 224, 224)
+    assert vqa.get_patch([50, 60, 40, 30], 300, 300, patch_scale=1.2) == O_get_patch([50, 60, 40, 30], 300, 300, 1.2)
+    text = vqa.free_form_inference(img, "Is the <object> red?", max_new_tokens=3, object_crops=torch.stack([crop]),
+                                   images_long=[False], objects_long=[True])
+    assert isinstance(text, str)
+    c = vqa.multiple_choices_inference(img, "What colour is the mug <object> ?", ["red", "blue mug", "green"],
+                                       object_crops=torch.stack([crop]), images_long=[False], objects_long=[True])
+    assert c in (0, 1, 2)
+
+
+def O_get_patch(bbox, w, h, scale):
+    from oracle import vqa_oracle as V
+    return V.get_patch(bbox, w, h, patch_scale=scale)

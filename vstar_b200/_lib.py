@@ -29,6 +29,7 @@ SIGNATURES = {
     "vsb_owl_merge_bf16": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p],
     "vsb_add_rows_bf16": [c_p, c_p, c_p, c_ll, c_i, c_ll, c_p],
     "vsb_cast_f32_bf16": [c_p, c_p, c_ll, c_p],
+    "vsb_nll_rows_f32": [c_p, c_ll, c_i, c_i, c_p, c_p, c_p],
     "vsb_argmax_rows_f32": [c_p, c_ll, c_i, c_i, c_p, c_p, c_p],
     "vsb_copy2d_b16": [c_p, c_ll, c_p, c_ll, c_ll, c_i, c_p],
     "vsb_flash_attn_bf16": [c_p, c_p, c_p, c_p, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],

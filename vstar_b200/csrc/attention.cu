@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(128) attn_small_kernel(const bf16* __restrict_
 #pragma unroll
   for (int d = 0; d < D; ++d) {
     const float a = warp_sum(acc[d] * c);
-    if (lane == (d & 31)) op[d] = f2bf(a * inv);
+    if (lane == (d & 31)) op[d] = f2bf(a * inv);   // (d & 31): spread the writers over the lanes
   }
 }
 
@@ -371,7 +371,7 @@ extern "C" int vsb_flash_attn_bf16(const void* q, const void* k, const void* v, 
 extern "C" int vsb_attn_small_bf16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o,
                                    long long ldo, int B, int H, int Nq, int Nk, int D, float scale, void* stream) {
   VSB_CHECK_ARG(q && k && v && o, "vsb_attn_small_bf16: null pointer");
-  VSB_CHECK_ARG(D == 16 || D == 32, "vsb_attn_small_bf16: head_dim %d unsupported (16/32)", D);
+  VSB_CHECK_ARG(D == 16 || D == 32 || D == 96, "vsb_attn_small_bf16: head_dim %d unsupported (16/32/96)", D);
   VSB_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0, "vsb_attn_small_bf16: ld must be multiples of 8");
   const long long warps = (long long)B * H * Nq;
   if (warps <= 0) return VSB_OK;
@@ -379,8 +379,10 @@ extern "C" int vsb_attn_small_bf16(const void* q, long long ldq, const void* k, 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (D == 16)
     attn_small_kernel<16><<<blocks, 128, 0, st>>>((const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (bf16*)o, ldo, B, H, Nq, Nk, scale);
-  else
+  else if (D == 32)
     attn_small_kernel<32><<<blocks, 128, 0, st>>>((const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (bf16*)o, ldo, B, H, Nq, Nk, scale);
+  else   // SEAL perceiver resampler: 16 heads x 96, 32 latents <-> 288 keys (LLaVA/llava/model/multimodal_projector/perceiver.py:25-77)
+    attn_small_kernel<96><<<blocks, 128, 0, st>>>((const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (bf16*)o, ldo, B, H, Nq, Nk, scale);
   VSB_LAUNCH_CHECK();
   return VSB_OK;
 }

@@ -320,6 +320,28 @@ __global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restric
   }
 }
 
+// negative log-likelihood of label[r] under softmax(logits[r, :]) (fp32): lse - logit[label]
+//   (CrossEntropyLoss of vstar_bench_eval.py:154-159, one row per option token)
+__global__ void __launch_bounds__(256) nll_rows_kernel(const float* __restrict__ x, long long ld, int n, const long long* __restrict__ labels,
+                                                       float* __restrict__ out) {
+  __shared__ float red[32];
+  const float* xr = x + (long long)blockIdx.x * ld;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, xr[i]);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += expf(xr[i] - mx);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    const long long lb = labels[blockIdx.x];
+    out[blockIdx.x] = (lb >= 0 && lb < n) ? (logf(s) + mx - xr[lb]) : 0.f;
+  }
+}
+
 }  // namespace
 
 #define STREAM(s) reinterpret_cast<cudaStream_t>(s)
@@ -420,6 +442,14 @@ extern "C" int vsb_cast_f32_bf16(const void* x, void* y, long long n, void* stre
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   cast_f32_bf16_kernel<<<blocks, 256, 0, STREAM(stream)>>>((const float*)x, (bf16*)y, n);
+  VSB_LAUNCH_CHECK();
+  return VSB_OK;
+}
+
+extern "C" int vsb_nll_rows_f32(const void* x, long long ld, int rows, int n, const void* labels_i64, void* out, void* stream) {
+  VSB_CHECK_ARG(x && labels_i64 && out && n > 0, "vsb_nll_rows_f32: bad args");
+  if (rows <= 0) return VSB_OK;
+  nll_rows_kernel<<<rows, 256, 0, STREAM(stream)>>>((const float*)x, ld, n, (const long long*)labels_i64, (float*)out);
   VSB_LAUNCH_CHECK();
   return VSB_OK;
 }

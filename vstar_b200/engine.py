@@ -32,10 +32,10 @@ def _pad8(n):
     return (n + 7) // 8 * 8
 
 
-class VSMWeights:
-    """Device-resident bf16 weights, re-laid-out for the kernels (fused QKV, interleaved gate/up, stacked
-    class-head rows, permuted conv taps).  Source = any callable name -> CPU/GPU tensor in the reference's
-    state_dict key layout, e.g. a loaded checkpoint dict's __getitem__."""
+class CoreWeights:
+    """Llama-7B + CLIP ViT-L/14 + mm_projector: shared by the VSM (visual search model) and the SEAL VQA LLM.
+    Device-resident bf16 weights re-laid-out for the kernels (fused QKV, interleaved gate/up).  Source = any callable
+    name -> CPU/GPU tensor in the reference's state_dict key layout."""
 
     def __init__(self, cfg: VSMConfig, get, device="cuda"):
         self.cfg = cfg
@@ -45,6 +45,7 @@ class VSMWeights:
         def g(name):
             return get(name).to(device=dev, dtype=BF).contiguous()
 
+        self._g = g
         c = cfg
         # ---- Llama
         self.embed = g("model.embed_tokens.weight")
@@ -70,6 +71,39 @@ class VSMWeights:
         self.clip = self._vit(g, "model.vision_tower.vision_tower.vision_model.", c.clip_layers + 1 + c.clip_select_layer
                               if c.clip_select_layer < 0 else c.clip_select_layer, c.clip_patch, "pre_layrnorm")
         self.mm_w, self.mm_b = g("model.mm_projector.weight"), g("model.mm_projector.bias")
+
+    @classmethod
+    def from_state_dict(cls, cfg, sd, device="cuda"):
+        return cls(cfg, lambda n: sd[n], device)
+
+    @staticmethod
+    def _vit(g, p, n_layers, patch, pre_name):
+        pw = g(p + "embeddings.patch_embedding.weight")
+        C = pw.shape[0]
+        K = 3 * patch * patch
+        Kp = _pad8(K)
+        w = torch.zeros((C, Kp), dtype=BF, device=pw.device)
+        w[:, :K] = pw.reshape(C, K)
+        layers = []
+        for i in range(n_layers):
+            q = f"{p}encoder.layers.{i}."
+            layers.append(dict(
+                wqkv=torch.cat([g(q + "self_attn.q_proj.weight"), g(q + "self_attn.k_proj.weight"), g(q + "self_attn.v_proj.weight")], 0).contiguous(),
+                bqkv=torch.cat([g(q + "self_attn.q_proj.bias"), g(q + "self_attn.k_proj.bias"), g(q + "self_attn.v_proj.bias")], 0).contiguous(),
+                wo=g(q + "self_attn.out_proj.weight"), bo=g(q + "self_attn.out_proj.bias"),
+                ln1=(g(q + "layer_norm1.weight"), g(q + "layer_norm1.bias")), ln2=(g(q + "layer_norm2.weight"), g(q + "layer_norm2.bias")),
+                w1=g(q + "mlp.fc1.weight"), b1=g(q + "mlp.fc1.bias"), w2=g(q + "mlp.fc2.weight"), b2=g(q + "mlp.fc2.bias")))
+        return dict(patch_w=w, Kpad=Kp, cls=g(p + "embeddings.class_embedding"), pos=g(p + "embeddings.position_embedding.weight"),
+                    pre=(g(p + pre_name + ".weight"), g(p + pre_name + ".bias")), layers=layers, C=C)
+
+
+class VSMWeights(CoreWeights):
+    """+ OWL-ViT-B/16, OWL heads, [LOC] query MLPs, SAM prompt encoder / mask decoder (stacked class-head rows,
+    permuted conv taps)."""
+
+    def __init__(self, cfg: VSMConfig, get, device="cuda"):
+        super().__init__(cfg, get, device)
+        g, c, dev = self._g, cfg, device
         self.owl = self._vit(g, "model.owlvit.vision_model.", c.owl_layers, c.owl_patch, "pre_layernorm")
         self.owl["post_w"], self.owl["post_b"] = g("model.owlvit.vision_model.post_layernorm.weight"), g("model.owlvit.vision_model.post_layernorm.bias")
         self.owl["merge_w"], self.owl["merge_b"] = g("model.owlvit.layer_norm.weight"), g("model.owlvit.layer_norm.bias")
@@ -117,26 +151,6 @@ class VSMWeights:
         self.hyper = [(g(hp + f"{j}.weight"), g(hp + f"{j}.bias")) for j in range(3)]
 
     @staticmethod
-    def _vit(g, p, n_layers, patch, pre_name):
-        pw = g(p + "embeddings.patch_embedding.weight")
-        C = pw.shape[0]
-        K = 3 * patch * patch
-        Kp = _pad8(K)
-        w = torch.zeros((C, Kp), dtype=BF, device=pw.device)
-        w[:, :K] = pw.reshape(C, K)
-        layers = []
-        for i in range(n_layers):
-            q = f"{p}encoder.layers.{i}."
-            layers.append(dict(
-                wqkv=torch.cat([g(q + "self_attn.q_proj.weight"), g(q + "self_attn.k_proj.weight"), g(q + "self_attn.v_proj.weight")], 0).contiguous(),
-                bqkv=torch.cat([g(q + "self_attn.q_proj.bias"), g(q + "self_attn.k_proj.bias"), g(q + "self_attn.v_proj.bias")], 0).contiguous(),
-                wo=g(q + "self_attn.out_proj.weight"), bo=g(q + "self_attn.out_proj.bias"),
-                ln1=(g(q + "layer_norm1.weight"), g(q + "layer_norm1.bias")), ln2=(g(q + "layer_norm2.weight"), g(q + "layer_norm2.bias")),
-                w1=g(q + "mlp.fc1.weight"), b1=g(q + "mlp.fc1.bias"), w2=g(q + "mlp.fc2.weight"), b2=g(q + "mlp.fc2.bias")))
-        return dict(patch_w=w, Kpad=Kp, cls=g(p + "embeddings.class_embedding"), pos=g(p + "embeddings.position_embedding.weight"),
-                    pre=(g(p + pre_name + ".weight"), g(p + pre_name + ".bias")), layers=layers, C=C)
-
-    @staticmethod
     def _box_bias(gsz):
         # /root/reference/VisualSearch/model/owlvit/owlvit.py:42-77 (fp32 numpy/torch constant)
         coords = np.stack(np.meshgrid(np.arange(1, gsz + 1), np.arange(1, gsz + 1)), axis=-1).astype(np.float32)
@@ -161,9 +175,6 @@ class VSMWeights:
         pe = torch.cat([torch.sin(cxy), torch.cos(cxy)], dim=-1)      # [g,g,256]
         return pe.reshape(gsz * gsz, -1).contiguous()
 
-    @classmethod
-    def from_state_dict(cls, cfg, sd, device="cuda"):
-        return cls(cfg, lambda n: sd[n], device)
 
 
 @dataclass
@@ -177,8 +188,10 @@ class CropResult:
     verified: bool
 
 
-class VSMEngine:
-    def __init__(self, weights: VSMWeights, max_batch=8, max_tokens=384):
+class LlamaClipCore:
+    """CLIP tower + Llama decoder on the sm_100a kernels with the fused-QKV cache; base of VSMEngine and VQAEngine."""
+
+    def __init__(self, weights: CoreWeights, max_batch=8, max_tokens=384):
         self.w = weights
         self.cfg = weights.cfg
         self.dev = weights.device
@@ -301,6 +314,9 @@ class VSMEngine:
         idx, _ = ops.argmax_rows(logits)
         return idx, hn, logits
 
+
+
+class VSMEngine(LlamaClipCore):
     # ------------------------------------------------------------------ heads
     def _mlp2(self, x, fc):
         h = ops.gemm(x, fc[0], bias=fc[1], epilogue=ops.EPI_RELU)

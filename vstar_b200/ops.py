@@ -196,6 +196,17 @@ def argmax_rows(x):
     return idx, val
 
 
+def nll_rows(logits, labels):
+    """logits fp32 [rows, V], labels int64 [rows] -> nll fp32 [rows]"""
+    _chk(logits, torch.float32)
+    p, rows, n, ld = _rows2d(logits)
+    assert labels.dtype == torch.int64 and labels.numel() == rows and labels.is_contiguous()
+    out = torch.empty((rows,), dtype=torch.float32, device=logits.device)
+    _lib.launches += 1
+    call("vsb_nll_rows_f32", p, ld, rows, n, labels.data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
 def copy2d(src, dst):
     """dst[:, :] = src[:, :] for 2-byte element 2-D views with unit inner stride."""
     ps, rows, cols, lds = _rows2d(src)

@@ -1,0 +1,327 @@
+"""SEAL VQA LLM on the sm_100a kernels — the model that brackets the visual search in `vstar_bench_eval.py`
+(SURVEY.md §8 rows a18-a20, §8f-1).
+
+  VQAWeights / VQAEngine : LlavaSearchLlamaForCausalLM (/root/reference/LLaVA/llava/model/language_model/llava_search_llama.py:56-141,
+                           llava_search_arch.py:83-279): CLIP-L -> BOTH projectors (linear "long" 256 tokens; LayerNorm ->
+                           PerceiverResampler(depth 6, 16 heads x 96, 32 latents) -> Linear "short" 32 tokens), <image>/<object>
+                           splicing with the long/short switches, Llama prefill / greedy decode on the fused-QKV cache, option
+                           scoring with the question prefix kept in the cache (vstar_bench_eval.py:116-165).
+  VQA_LLM                : drop-in mirror of `vstar_bench_eval.VQA_LLM` (free_form_inference, multiple_choices_inference,
+                           get_patch, get_object_crop).
+
+The reference runs this model in fp16 (LLaVA/llava/model/builder.py:43); the kernels here are bf16 with fp32
+accumulation — the tolerance is stated in tests/test_vqa_gpu.py.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .config import VSMConfig
+from .engine import CoreWeights, LlamaClipCore
+from .vsm import CLIP_MEAN, SyntheticTokenizer, _normalize_into
+
+BF = torch.bfloat16
+IMAGE_TOKEN_INDEX = -200
+OBJECT_TOKEN_INDEX = -300
+DEFAULT_IMAGE_TOKEN = "<image>"
+DEFAULT_OBJECT_TOKEN = "<object>"
+
+VICUNA_V1_SYSTEM = ("A chat between a curious user and an artificial intelligence assistant. "
+                    "The assistant gives helpful, detailed, and polite answers to the user's questions.")
+
+
+def build_prompt_v1(question_with_image_token, answer=None):
+    """conv_templates['v1'] (LLaVA/llava/conversation.py:252-262; SeparatorStyle.TWO, sep ' ', sep2 '</s>')"""
+    ret = VICUNA_V1_SYSTEM + " " + "USER: " + question_with_image_token + " "
+    if answer:
+        ret += "ASSISTANT: " + answer + "</s>"
+    else:
+        ret += "ASSISTANT:"
+    return ret
+
+
+def tokenizer_image_object_token(prompt, tokenizer, image_token_index=IMAGE_TOKEN_INDEX, object_token_index=OBJECT_TOKEN_INDEX):
+    """LLaVA/llava/mm_utils.py:65-87 (behaviour kept verbatim: defines the token sequence)"""
+    prompt_chunks = []
+    for prompt_chunk in prompt.split("<image>"):
+        prompt_chunks.extend(prompt_chunk.split("<object>"))
+    prompt_chunks = [tokenizer(chunk).input_ids for chunk in prompt_chunks]
+
+    def insert_separator(X, seps):
+        return [ele for sublist in zip(X, seps) for ele in sublist][:-1]
+
+    input_ids = []
+    offset = 0
+    if len(prompt_chunks) > 0 and len(prompt_chunks[0]) > 0 and prompt_chunks[0][0] == tokenizer.bos_token_id:
+        offset = 1
+        input_ids.append(prompt_chunks[0][0])
+    sep = [[image_token_index] * (offset + 1)] + [[object_token_index] * (offset + 1)] * (len(prompt_chunks) - 1)
+    for x in insert_separator(prompt_chunks, sep):
+        input_ids.extend(x[offset:])
+    return input_ids
+
+
+class VQAWeights(CoreWeights):
+    """CoreWeights + the object projector `model.mm_projector_object.{0,1,2}` (multimodal_projector/builder.py:54-68)"""
+
+    def __init__(self, cfg: VSMConfig, get, device="cuda"):
+        super().__init__(cfg, get, device)
+        g = self._g
+        p = "model.mm_projector_object."
+        self.pj_ln = (g(p + "0.weight"), g(p + "0.bias"))
+        self.latents = g(p + "1.latents")
+        self.media_pos = g(p + "1.media_pos_emb").reshape(1, -1).contiguous()
+        self.pj_layers = []
+        for i in range(6):
+            a, f = f"{p}1.layers.{i}.0.", f"{p}1.layers.{i}.1."
+            self.pj_layers.append(dict(
+                nm=(g(a + "norm_media.weight"), g(a + "norm_media.bias")), nl=(g(a + "norm_latents.weight"), g(a + "norm_latents.bias")),
+                wq=g(a + "to_q.weight"), wkv=g(a + "to_kv.weight"), wo=g(a + "to_out.weight"),
+                ffn=(g(f + "0.weight"), g(f + "0.bias")), w1=g(f + "1.weight"), w2=g(f + "3.weight")))
+        self.pj_norm = (g(p + "1.norm.weight"), g(p + "1.norm.bias"))
+        self.pj_out = (g(p + "2.weight"), g(p + "2.bias"))
+
+
+class VQAEngine(LlamaClipCore):
+    HEADS, DHEAD, NLAT = 16, 96, 32
+
+    def __init__(self, weights: VQAWeights, max_tokens=1536):
+        super().__init__(weights, max_tokens=max_tokens)
+
+    # ------------------------------------------------------------------ projectors
+    def project_both(self, pixels):
+        """encode_images / project_features (llava_search_arch.py:83-93): pixels [n,3,224,224] bf16 ->
+        (long [n*256, d], short [n*32, d])"""
+        c, w = self.cfg, self.w
+        n = pixels.shape[0]
+        ct, S = self.clip_tokens(pixels)                                   # [n*257, C] incl. CLS
+        P = S - 1
+        rows = torch.arange(n * S, device=self.dev).view(n, S)[:, 1:].reshape(-1).contiguous()
+        feats = ops.gather_rows(rows, ct)                                  # hidden_states[-2][:, 1:]
+        long_ = ops.gemm(feats, w.mm_w, bias=w.mm_b)
+        C = feats.shape[1]
+        inner = self.HEADS * self.DHEAD
+        x = ops.layernorm(feats, w.pj_ln[0], w.pj_ln[1], 1e-5)
+        x = ops.add_rows(x, w.media_pos)                                   # + media_pos_emb[:1]
+        lat = w.latents.repeat(n, 1).contiguous()                          # [n*32, C]
+        NK = P + self.NLAT
+        kv = torch.empty((n * NK, 2 * inner), dtype=BF, device=self.dev)
+        for L in w.pj_layers:
+            xm = ops.layernorm(x, L["nm"][0], L["nm"][1], 1e-5)
+            lt = ops.layernorm(lat, L["nl"][0], L["nl"][1], 1e-5)
+            q = ops.gemm(lt, L["wq"])
+            # to_kv(cat(media, latents)): two GEMMs scatter their rows into one [n, P+32, 2*inner] buffer
+            ops.gemm(xm, L["wkv"], out=kv, rows_per_group=P, group_stride=NK, group_offset=0)
+            ops.gemm(lt, L["wkv"], out=kv, rows_per_group=self.NLAT, group_stride=NK, group_offset=P)
+            o = ops.attn_small(q, kv[:, :inner], kv[:, inner:], n, self.HEADS, self.NLAT, NK, self.DHEAD, self.DHEAD ** -0.5)
+            lat = ops.gemm(o, L["wo"], residual=lat)
+            h = ops.layernorm(lat, L["ffn"][0], L["ffn"][1], 1e-5)
+            h = ops.gemm(h, L["w1"], epilogue=ops.EPI_GELU)
+            lat = ops.gemm(h, L["w2"], residual=lat)
+        res = ops.layernorm(lat, w.pj_norm[0], w.pj_norm[1], 1e-5)
+        short = ops.gemm(res, w.pj_out[0], bias=w.pj_out[1])
+        return long_, short
+
+    # ------------------------------------------------------------------ splice (llava_search_arch.py:139-216)
+    def build_embeds(self, input_ids, image, object_crops=None, images_long=None, objects_long=None):
+        """input_ids: python list with one -200 and k -300 placeholders -> embeds [T, d] on the device"""
+        c = self.cfg
+        ids = list(input_ids)
+        img_long, img_short = self.project_both(image)
+        if object_crops is not None and len(object_crops) > 0:
+            obj_long, obj_short = self.project_both(object_crops)
+        segs = []                                   # ("ids", list) | ("feat", tensor [m,d])
+        s = ids.index(IMAGE_TOKEN_INDEX)
+        use_long = images_long is None or bool(images_long[0])
+        segs += [("ids", ids[:s]), ("feat", img_long if use_long else img_short)]
+        cur = ids[s + 1:]
+        oi = 0
+        while OBJECT_TOKEN_INDEX in cur:
+            s = cur.index(OBJECT_TOKEN_INDEX)
+            short = objects_long is None or not bool(objects_long[oi])
+            f = obj_short[oi * 32:(oi + 1) * 32] if short else obj_long[oi * c.clip_tokens:(oi + 1) * c.clip_tokens]
+            segs += [("ids", cur[:s]), ("feat", f)]
+            oi += 1
+            cur = cur[s + 1:]
+        if cur:
+            segs.append(("ids", cur))
+        T = sum(len(v) if k == "ids" else v.shape[0] for k, v in segs)
+        x = torch.empty((T, c.hidden), dtype=BF, device=self.dev)
+        t = 0
+        for k, v in segs:
+            n = len(v) if k == "ids" else v.shape[0]
+            if n == 0:
+                continue
+            if k == "ids":
+                ops.gather_rows(torch.tensor(v, dtype=torch.int64, device=self.dev), self.w.embed, out=x[t:t + n])
+            else:
+                ops.copy2d(v, x[t:t + n])
+            t += n
+        return x
+
+    # ------------------------------------------------------------------ LM
+    def prefill_embeds(self, x):
+        """x [T,d] (consumed in place) -> residual stream after all layers; cache positions 0..T"""
+        T = x.shape[0]
+        assert T <= self.max_tokens, (T, self.max_tokens)
+        self._ensure_cache(1, self.max_tokens)
+        self._llm_layers(x, 1, T, 0, self.max_tokens)
+        return x
+
+    def append_tokens(self, tokens, past):
+        """run `tokens` (python list) on top of `past` cached positions -> logits fp32 [n, V] for every new position"""
+        ids = torch.tensor(tokens, dtype=torch.int64, device=self.dev)
+        x = ops.gather_rows(ids, self.w.embed)
+        self._llm_layers(x, 1, len(tokens), past, self.max_tokens)
+        hn = ops.rmsnorm(x, self.w.final_norm, self.cfg.rms_eps)
+        return ops.gemm(hn, self.w.lm_head, out_dtype=torch.float32)
+
+    def last_logits(self, x):
+        rows = torch.tensor([x.shape[0] - 1], dtype=torch.int64, device=self.dev)
+        hn, am, logits = self._logits_rows(x, rows)
+        return logits
+
+    def generate(self, input_ids, image, object_crops=None, images_long=None, objects_long=None, max_new_tokens=200, eos_token_id=2,
+                 stop_ids=None):
+        """greedy `model.generate(use_cache=True, do_sample=False)` (vstar_bench_eval.py:91-103) -> list of new token ids"""
+        x = self.build_embeds(input_ids, image, object_crops, images_long, objects_long)
+        T = x.shape[0]
+        self.prefill_embeds(x)
+        logits = self.last_logits(x)
+        out = []
+        past = T
+        for _ in range(max_new_tokens):
+            nxt = int(ops.argmax_rows(logits)[0][0])
+            out.append(nxt)
+            if nxt == eos_token_id or (stop_ids and out[-len(stop_ids):] == list(stop_ids)) or past >= self.max_tokens - 1:
+                break
+            logits = self.append_tokens([nxt], past)
+            past += 1
+        return out
+
+    def option_losses(self, question_ids, options_ids, image, object_crops=None, images_long=None, objects_long=None):
+        """multiple_choices_inference core (vstar_bench_eval.py:127-163): the question prefix is prefilled ONCE; every
+        option is appended on top of the cached prefix (its rows overwrite the previous option's) and scored by the mean
+        token NLL.  Returns (losses fp32 [n_options] on host, argmin)."""
+        x = self.build_embeds(question_ids, image, object_crops, images_long, objects_long)
+        Tq = x.shape[0]
+        self.prefill_embeds(x)
+        q_last = self.last_logits(x)                                  # predicts the first option token
+        losses = []
+        for opt in options_ids:
+            opt = list(opt)
+            lg = self.append_tokens(opt, Tq)                           # [n, V]; row i predicts token i+1
+            rows = torch.cat([q_last, lg[:-1]], dim=0).contiguous()
+            nll = ops.nll_rows(rows, torch.tensor(opt, dtype=torch.int64, device=self.dev))
+            losses.append(nll.mean())
+        losses = torch.stack(losses).cpu()
+        return losses, int(losses.argmin())
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def _clip_preprocess(pil_img, size=224):
+    """CLIPImageProcessor.preprocess of the reference (shortest edge 224 bicubic, centre crop 224, /255, mean/std)"""
+    from PIL import Image
+    img = pil_img.convert("RGB")
+    w, h = img.size
+    short = min(w, h)
+    if (w, h) != (size, size):
+        nw, nh = int(w * size / short), int(h * size / short)
+        img = img.resize((nw, nh), resample=Image.BICUBIC)
+        left, top = (nw - size) // 2, (nh - size) // 2
+        img = img.crop((left, top, left + size, top + size))
+    out = torch.empty((3, size, size), dtype=torch.float32)
+    _normalize_into(np.array(img), out)
+    return out
+
+
+class _Proc:
+    crop_size = {"height": 224, "width": 224}
+    image_mean = list(CLIP_MEAN)
+
+    def preprocess(self, image, return_tensors="pt"):
+        return {"pixel_values": [_clip_preprocess(image)]}
+
+
+class VQA_LLM:
+    """Same surface as /root/reference/vstar_bench_eval.py:38-165."""
+
+    def __init__(self, args=None, engine: VQAEngine = None, tokenizer=None, conv_type="v1"):
+        if engine is None:
+            import os
+            from .vsm import config_from_hf, open_checkpoint
+            path = args.vqa_model_path
+            if not os.path.isdir(str(path)):
+                raise FileNotFoundError("VQA_LLM(args): args.vqa_model_path must be a local checkpoint directory")
+            from transformers import AutoTokenizer
+            tokenizer = AutoTokenizer.from_pretrained(path, use_fast=False)
+            cfg = config_from_hf(path)
+            main = open_checkpoint(path)
+            engine = VQAEngine(VQAWeights(cfg, main))
+            conv_type = getattr(args, "conv_type", "v1")
+        self.engine = self.model = engine
+        self.tokenizer = tokenizer if tokenizer is not None else SyntheticTokenizer(engine.cfg)
+        self.image_processor = _Proc()
+        self.context_len = 2048
+        self.conv_type = conv_type
+        self.eos = getattr(self.tokenizer, "eos_token_id", 2)
+
+    def get_patch(self, bbox, image_width, image_height, patch_size=224, patch_scale=None):
+        object_width = int(np.ceil(bbox[2]))
+        object_height = int(np.ceil(bbox[3]))
+        cx = int(bbox[0] + bbox[2] / 2)
+        cy = int(bbox[1] + bbox[3] / 2)
+        if patch_scale is None:
+            pw, ph = max(object_width, patch_size), max(object_height, patch_size)
+        else:
+            pw, ph = int(object_width * patch_scale), int(object_height * patch_scale)
+        left = max(0, cx - pw // 2)
+        right = min(left + pw, image_width)
+        top = max(0, cy - ph // 2)
+        bottom = min(top + ph, image_height)
+        return [left, top, right, bottom]
+
+    def get_object_crop(self, image, bbox, patch_scale):
+        b = self.get_patch(bbox, image.width, image.height, patch_scale=patch_scale)
+        crop = image.crop((b[0], b[1], b[2], b[3])).resize((224, 224))
+        return _clip_preprocess(crop)
+
+    def _pixels(self, image, object_crops):
+        img = _clip_preprocess(image).unsqueeze(0).to(self.engine.dev)
+        img = ops.cast_f32_bf16(img.contiguous())
+        crops = None
+        if object_crops is not None and len(object_crops) > 0:
+            crops = ops.cast_f32_bf16(torch.as_tensor(object_crops).float().to(self.engine.dev).contiguous())
+        return img, crops
+
+    @torch.inference_mode()
+    def free_form_inference(self, image, question, temperature=0, top_p=None, num_beams=1, max_new_tokens=200, object_crops=None,
+                            images_long=None, objects_long=None):
+        if temperature and temperature > 0:
+            raise NotImplementedError("sampling is not on the V*Bench path (temperature=0, vstar_bench_eval.py:196)")
+        prompt = build_prompt_v1(DEFAULT_IMAGE_TOKEN + "\n" + question)
+        stop_str = "</s>"
+        ids = tokenizer_image_object_token(prompt, self.tokenizer)
+        kw = self.tokenizer(stop_str).input_ids
+        if len(kw) > 1 and kw[0] == self.tokenizer.bos_token_id:
+            kw = kw[1:]
+        img, crops = self._pixels(image, object_crops)
+        out = self.engine.generate(ids, img, crops, images_long, objects_long, max_new_tokens, self.eos, stop_ids=kw)
+        text = self.tokenizer.batch_decode([out], skip_special_tokens=True)[0].strip()
+        if text.endswith(stop_str):
+            text = text[:-len(stop_str)]
+        return text.strip()
+
+    @torch.inference_mode()
+    def multiple_choices_inference(self, image, question, options, object_crops=None, images_long=None, objects_long=None):
+        qs = DEFAULT_IMAGE_TOKEN + "\n" + question
+        q_ids = tokenizer_image_object_token(build_prompt_v1(qs), self.tokenizer)
+        opt_ids = []
+        for option in options:
+            full = tokenizer_image_object_token(build_prompt_v1(qs, option), self.tokenizer)
+            opt_ids.append(full[len(q_ids):])
+        img, crops = self._pixels(image, object_crops)
+        losses, choice = self.engine.option_losses(q_ids, opt_ids, img, crops, images_long, objects_long)
+        return choice

@@ -362,3 +362,112 @@ class VSM:
             ev.low_res = r["low_res"]
             out.append(ev)
         return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# model-loading API mirror: VSMForCausalLM.from_pretrained / .inference / .model_forward
+# ----------------------------------------------------------------------------------------------------------------
+class _VisionTowerHandle:
+    """what `vsm_model.get_model().get_vision_tower()` hands to the reference wrapper (visual_search.py:160-162)"""
+
+    def __init__(self):
+        self.image_processor = None
+
+    def cuda(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+
+class _Cfg:
+    pass
+
+
+class VSMForCausalLM:
+    """Drop-in for /root/reference/VisualSearch/model/VSM.py:162-553 (inference paths only) on the sm_100a engine."""
+
+    def __init__(self, engine: VSMEngine, vision_tower_name="openai/clip-vit-large-patch14"):
+        self.engine = engine
+        self.cfg = engine.cfg
+        self.loc_token_idx = engine.cfg.loc_token_idx
+        self.config = _Cfg()
+        self.config.vision_tower = vision_tower_name
+        self.config.mm_vision_tower = vision_tower_name
+        self.config.vocab_size = engine.cfg.vocab
+        self._tower = _VisionTowerHandle()
+
+    @classmethod
+    def from_pretrained(cls, version, low_cpu_mem_usage=True, vision_tower="openai/clip-vit-large-patch14", loc_token_idx=None,
+                        torch_dtype=torch.bfloat16, device_map="cuda", is_eval=True, **kwargs):
+        """visual_search.py:157-159.  `version` = local checkpoint dir (HF shards, key layout of
+        merge_lora_weights_and_save_hf_model.py:143-151); CLIP weights come from the `vision_tower` directory."""
+        if torch_dtype != torch.bfloat16:
+            raise NotImplementedError("the sm_100a kernels compute in bf16 (the reference loads the VSM in bf16 too)")
+        cfg = config_from_hf(version)
+        if loc_token_idx is not None:
+            cfg.loc_token_idx = int(loc_token_idx)
+        main = open_checkpoint(version)
+        clip = open_checkpoint(vision_tower)
+
+        def get(name):
+            pfx = "model.vision_tower.vision_tower."
+            return clip(name[len(pfx):]) if name.startswith(pfx) else main(name)
+
+        device = "cuda" if device_map in ("cuda", "auto") else device_map
+        return cls(VSMEngine(VSMWeights(cfg, get, device=device)), vision_tower)
+
+    # -- HF-style accessors used by the reference wrapper
+    def get_model(self):
+        return self
+
+    def initialize_vision_modules(self, cfg):
+        return None                       # CLIP is part of the engine weights already
+
+    def get_vision_tower(self):
+        return self._tower
+
+    def eval(self):
+        return self
+
+    def _ids_rows(self, ids_1d, T, img_pos):
+        c = self.cfg
+        return [(k - 1) + c.clip_tokens - 1 for k in (ids_1d == c.loc_token_idx).nonzero().flatten().tolist()]
+
+    @torch.inference_mode()
+    def model_forward(self, images, images_clip, input_ids, original_size_list=None, label_list=None, inference=True, **_unused):
+        """VSM.py:201-364 with inference=True (batch of teacher-forced samples sharing one length)"""
+        assert inference, "training losses are outside the hot path"
+        out = self.engine.model_forward(images.to(torch.bfloat16), images_clip.to(torch.bfloat16), input_ids)
+        sizes = original_size_list if original_size_list is not None else [tuple(l.shape) for l in label_list]
+        pred_masks = []
+        for b in range(input_ids.shape[0]):
+            locs = [k for k, cb in enumerate(out["crop_of_loc"]) if cb == b]
+            h, w = sizes[b]
+            pred_masks.append(torch.stack([ops.heatmap(out["low_res_masks"][k].contiguous(), int(h), int(w), clamp=False, with_stats=False)[0] for k in locs]))
+        return {"pred_masks": pred_masks, "gt_masks": None, "pred_logits": out["pred_logits"].unsqueeze(-1),
+                "pred_boxes": out["pred_boxes"], "gt_bboxes": None}
+
+    @torch.inference_mode()
+    def inference(self, images_clip, images, input_ids, resize_list, original_size_list, max_new_tokens=32, tokenizer=None, mode="vqa"):
+        """VSM.py:438-553: greedy generate, then (mode != 'vqa') the seg / det branches.  Returns
+        (output_ids [1,L] | None, [pred_masks [n_loc,h,w]] | None, {'pred_logits','pred_boxes'} | None)."""
+        assert mode in ["vqa", "segmentation", "detection"]
+        assert input_ids.shape[0] == 1, "the reference wrapper evaluates one crop per call"
+        eos = getattr(tokenizer, "eos_token_id", 2) if tokenizer is not None else 2
+        ic = images_clip.to(torch.bfloat16)
+        out_ids, _ = self.engine.generate(input_ids.cpu(), ic, max_new_tokens=max_new_tokens, eos_token_id=eos)
+        output_ids = torch.tensor([out_ids], dtype=torch.int64, device=input_ids.device)
+        if mode == "vqa":
+            return output_ids, None, None
+        if self.loc_token_idx not in out_ids:
+            # the reference returns empty lists here and its wrapper then fails with IndexError (visual_search.py:209-211)
+            return None, [], None
+        ids = torch.tensor([out_ids[:-1]], dtype=torch.int64, device=self.engine.dev)     # last generate step's input (VSM.py:459)
+        out = self.engine.model_forward(images.to(torch.bfloat16), ic, ids, mode=mode)
+        h, w = original_size_list[0]
+        pm = torch.stack([ops.heatmap(out["low_res_masks"][k].contiguous(), int(h), int(w), clamp=False, with_stats=False)[0]
+                          for k in range(out["low_res_masks"].shape[0])])
+        if mode == "segmentation":
+            return None, [pm], None
+        return None, [pm], {"pred_logits": out["pred_logits"].unsqueeze(-1), "pred_boxes": out["pred_boxes"]}
