@@ -9,7 +9,7 @@ import torch
 from vstar_b200 import ops, _lib
 
 BF = torch.bfloat16
-flush = torch.empty(256 * 1024 * 1024, dtype=torch.int8, device="cuda")
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.int8, device="cuda") if torch.cuda.is_available() else None
 
 
 def timeit(fn, iters=10, warmup=3):
