@@ -157,7 +157,8 @@ def llama_forward(sd, cfg: VSMConfig, embeds):
     B, T, d = embeds.shape
     H, hd = cfg.n_heads, cfg.head_dim
     cos, sin = rope_cos_sin(T, hd, cfg.rope_theta, embeds.dtype)
-    mask = torch.full((T, T), float("-inf"), dtype=embeds.dtype).triu(1)
+    cos, sin = cos.to(embeds.device), sin.to(embeds.device)
+    mask = torch.full((T, T), float("-inf"), dtype=embeds.dtype, device=embeds.device).triu(1)
     x = embeds
     for i in range(cfg.n_layers):
         p = f"model.layers.{i}."
@@ -216,7 +217,7 @@ def greedy_generate(sd, cfg, input_ids, images_clip, max_new_tokens=100, eos_tok
         argmaxes.append(nxt)
         if forced_ids is not None and step < len(forced_ids):
             nxt = int(forced_ids[step])
-        ids = torch.cat([ids, torch.tensor([[nxt]], dtype=ids.dtype)], dim=1)
+        ids = torch.cat([ids, torch.tensor([[nxt]], dtype=ids.dtype, device=ids.device)], dim=1)
         if nxt == eos_token_id:
             break
     return ids, hidden, argmaxes
@@ -227,7 +228,7 @@ def greedy_generate(sd, cfg, input_ids, images_clip, max_new_tokens=100, eos_tok
 # --------------------------------------------------------------------------
 def loc_mask_from_output_ids(output_ids, loc_idx):
     m = output_ids[:, 1:] == loc_idx
-    return torch.cat([torch.zeros((m.shape[0], 255), dtype=torch.bool), m], dim=1)
+    return torch.cat([torch.zeros((m.shape[0], 255), dtype=torch.bool, device=m.device), m], dim=1)
 
 
 def text_fcs(sd, which, hidden):
@@ -243,7 +244,7 @@ def text_fcs(sd, which, hidden):
 # --------------------------------------------------------------------------
 def dense_pe(sd, g):
     G = sd["model.prompt_encoder.pe_layer.positional_encoding_gaussian_matrix"]
-    grid = torch.ones((g, g), dtype=G.dtype)
+    grid = torch.ones((g, g), dtype=G.dtype, device=G.device)
     y = (grid.cumsum(dim=0) - 0.5) / g
     x = (grid.cumsum(dim=1) - 0.5) / g
     c = torch.stack([x, y], dim=-1)
@@ -381,7 +382,7 @@ def owl_heads(sd, cfg, feature_map_i, det_queries):
     logits = (logits + shift) * scale
     p = "model.owlvit.box_head."
     b = _lin(sd, p + "dense2", F.gelu(_lin(sd, p + "dense1", F.gelu(_lin(sd, p + "dense0", feats)))))
-    b = b + owl_box_bias(g)            # in-place += in the reference: result stays in activation dtype
+    b = b + owl_box_bias(g).to(b.device)   # in-place += in the reference: result stays in activation dtype
     b = b.to(feats.dtype) if feats.dtype != torch.float32 else b
     return logits, torch.sigmoid(b)
 
