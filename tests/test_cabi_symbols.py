@@ -1,0 +1,38 @@
+"""The C-ABI shared library loads (no GPU needed) and exports every entry point include/vstar_b200.h declares; the
+ctypes table in vstar_b200/_lib.py covers exactly those symbols.  No compute calls here."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared():
+    src = open(os.path.join(ROOT, "include", "vstar_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vsb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from vstar_b200 import _lib, build
+    build.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/vstar_b200.h but not exported"
+    table = set(_lib.SIGNATURES) | {"vsb_last_error", "vsb_version"}
+    assert table == set(names), (sorted(table - set(names)), sorted(set(names) - table))
+    loaded = _lib.load()
+    assert loaded.vsb_version() >= 100 and isinstance(loaded.vsb_last_error(), bytes)
+
+
+def test_ops_refuse_cpu_tensors_without_fallback():
+    import pytest
+    import torch
+    from vstar_b200 import ops
+    from vstar_b200._lib import VsbError
+    with pytest.raises(VsbError):
+        ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+    with pytest.raises(VsbError):
+        ops.layernorm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.ones(8, dtype=torch.bfloat16), torch.zeros(8, dtype=torch.bfloat16), 1e-5)
