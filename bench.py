@@ -5,7 +5,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
     python bench.py --impl reference ...          # the reference's CPU path (oracle port) on the host cores
 
-A "step" = one pass of the hot path over one batch of synthetic input: `--searches` independent guided visual
+A "step" = one pass of the hot path over one batch of synthetic input: `--searches` (32) independent guided visual
 searches (BASELINE.json configs[1]: 1024x1024 synthetic images, smallest_size 512 => root + 4 crops each, depth 2,
 bf16), run in lock-step so their crop frontiers share GPU batches; every crop evaluation = CLIP ViT-L/14 -> projector
 -> Vicuna-7B-shaped prefill (draft-verified answer) -> OWL-ViT-B/16 -> SAM prompt/mask decoder -> OWL heads -> heat-map
@@ -37,10 +37,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--searches", type=int, default=8, help="concurrent searches per step per GPU")
+    ap.add_argument("--searches", type=int, default=32, help="concurrent searches per step per GPU")
     ap.add_argument("--image", type=int, default=1024)
     ap.add_argument("--smallest", type=int, default=512)
-    ap.add_argument("--batch", type=int, default=32, help="frontier batch (crops per engine call)")
+    ap.add_argument("--batch", type=int, default=64, help="frontier batch (crops per engine call)")
     ap.add_argument("--tiny", action="store_true", help="tiny model (debug only; not a valid bench)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -104,6 +104,12 @@ def cpu_reference_sample(llama_layers=2, tiny=False):
     from oracle import vsm_oracle as O
     from vstar_b200.config import VSMConfig, tiny_config
     from vstar_b200 import synth
+    # all host threads (torchrun exports OMP_NUM_THREADS=1, which would silently make this a 1-core baseline)
+    try:
+        n_threads = len(os.sched_getaffinity(0))
+    except Exception:
+        n_threads = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n_threads))
     cfg = tiny_config() if tiny else VSMConfig()
     full_layers = cfg.n_layers
     run_layers = min(llama_layers, full_layers)
