@@ -106,3 +106,31 @@ def test_vqa_llm_wrapper_api(setup):
 def O_get_patch(bbox, w, h, scale):
     from oracle import vqa_oracle as V
     return V.get_patch(bbox, w, h, patch_scale=scale)
+
+
+def test_full_seal_loop_tiny(setup):
+    """VQA LLM -> missing objects -> lock-step guided searches (CUDA VSM) -> object crops -> option scoring"""
+    from PIL import Image
+    from oracle import vsm_oracle as O2
+    from vstar_b200.engine import VSMEngine, VSMWeights
+    from vstar_b200.seal import MISSING_OBJECTS_MSG, seal_answer
+    from vstar_b200.vqa import VQA_LLM
+    from vstar_b200.vsm import VSM
+    V, O, cfg, sd, eng = setup
+    vsd = O2.synthetic_state_dict(cfg, seed=1234)
+    prompt, ans = O2.synthetic_prompt(cfg, n_text=24, seed=5)
+
+    class V2(VSM):
+        def _ids(self, q):
+            return prompt[0].tolist()
+
+    vsm = V2(engine=VSMEngine(VSMWeights.from_state_dict(cfg, vsd)), forced_answer_ids=ans.tolist(), frontier_batch=8)
+    vqa = VQA_LLM(engine=eng)
+    img = Image.fromarray(np.random.default_rng(9).integers(0, 256, (480, 700, 3), dtype=np.uint8), "RGB")
+    res = seal_answer(vqa, vsm, img, "What colour is the mug?", ["red", "blue", "green", "white"],
+                      prediction_override=MISSING_OBJECTS_MSG + " mug, laptop.",
+                      search_kwargs=dict(confidence_high=2.0, target_cue_threshold=-1e9, target_cue_threshold_minimum=-1e9))
+    assert res["missing_objects"] == ["mug", "laptop"] and len(res["search_result"]) == 2
+    assert res["option_chosen"] in (0, 1, 2, 3) and all(len(r["bbox"]) == 4 for r in res["search_result"])
+    res2 = seal_answer(vqa, vsm, img, "q", ["a", "b"], prediction_override="It is red.")
+    assert res2["missing_objects"] == [] and res2["option_chosen"] in (0, 1)
