@@ -8,59 +8,73 @@
 
 namespace {
 
-// ------------------------------------------------------------------ LayerNorm
-// y = (x - mean) * rsqrt(var + eps) * w + b ; fp32 statistics (two-pass in registers),
-// bf16 in/out.  One block (128 threads) per row; cols <= 128*8*VEC_ITERS.
-template <int MAX_V>   // number of 8-element vectors each thread may hold
-__global__ void __launch_bounds__(128) layernorm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ w,
-                                                        const bf16* __restrict__ b, bf16* __restrict__ y, long long ldy,
-                                                        int rows, int cols, float eps, int act) {
-  __shared__ float red[32];
-  const int row = blockIdx.x;
-  if (row >= rows) return;
-  const bf16* xr = x + (long long)row * ldx;
-  bf16* yr = y + (long long)row * ldy;
-  const int nvec = cols >> 3;
-  float v[MAX_V][8];
-  float s = 0.f;
+// ------------------------------------------------------------------ LayerNorm / RMSNorm: ONE WARP PER ROW
+// The whole row lives in the warp's registers (MAXV 16-byte vectors per lane), statistics by warp shuffles only - no
+// shared memory, no __syncthreads - and every lane has MAXV independent 16 B loads in flight, which is what an HBM-bound
+// row kernel needs (the previous block-per-row version sat at ~2.5 TB/s).
+template <int MAXV>
+__device__ __forceinline__ int load_row(const bf16* __restrict__ xr, int nvec, int lane, float (*v)[8]) {
+  int cnt = 0;
 #pragma unroll
-  for (int i = 0; i < MAX_V; ++i) {
-    int vi = threadIdx.x + i * 128;
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + i * 32;
     if (vi < nvec) {
-      uint4 u = *reinterpret_cast<const uint4*>(xr + vi * 8);
+      const uint4 u = *reinterpret_cast<const uint4*>(xr + vi * 8);
       float2 t;
       t = unpack_bf16x2(u.x); v[i][0] = t.x; v[i][1] = t.y;
       t = unpack_bf16x2(u.y); v[i][2] = t.x; v[i][3] = t.y;
       t = unpack_bf16x2(u.z); v[i][4] = t.x; v[i][5] = t.y;
       t = unpack_bf16x2(u.w); v[i][6] = t.x; v[i][7] = t.y;
+      ++cnt;
+    }
+  }
+  return cnt;
+}
+
+__device__ __forceinline__ void unpack8(const uint4 u, float* f) {
+  float2 t;
+  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+
+// y = (x - mean) * rsqrt(var + eps) * w + b ; fp32 statistics (two-pass over registers), bf16 in/out, optional GELU
+template <int MAXV>
+__global__ void __launch_bounds__(128) layernorm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ w,
+                                                        const bf16* __restrict__ b, bf16* __restrict__ y, long long ldy,
+                                                        int rows, int cols, float eps, int act) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const bf16* xr = x + (long long)row * ldx;
+  bf16* yr = y + (long long)row * ldy;
+  const int nvec = cols >> 3;
+  float v[MAXV][8];
+  load_row<MAXV>(xr, nvec, lane, v);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (lane + i * 32 < nvec) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[i][j];
     }
-  }
-  const float mean = block_sum(s, red) / (float)cols;
+  const float mean = warp_sum(s) / (float)cols;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_V; ++i) {
-    int vi = threadIdx.x + i * 128;
-    if (vi < nvec) {
+  for (int i = 0; i < MAXV; ++i)
+    if (lane + i * 32 < nvec) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { float d = v[i][j] - mean; sq += d * d; }
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; sq += d * d; }
     }
-  }
-  const float rstd = rsqrtf(block_sum(sq, red) / (float)cols + eps);
+  const float rstd = rsqrtf(warp_sum(sq) / (float)cols + eps);
 #pragma unroll
-  for (int i = 0; i < MAX_V; ++i) {
-    int vi = threadIdx.x + i * 128;
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + i * 32;
     if (vi < nvec) {
-      uint4 wu = __ldg(reinterpret_cast<const uint4*>(w + vi * 8));
-      uint4 bu = __ldg(reinterpret_cast<const uint4*>(b + vi * 8));
-      float wf[8], bfv[8];
-      float2 t;
-      t = unpack_bf16x2(wu.x); wf[0] = t.x; wf[1] = t.y; t = unpack_bf16x2(wu.y); wf[2] = t.x; wf[3] = t.y;
-      t = unpack_bf16x2(wu.z); wf[4] = t.x; wf[5] = t.y; t = unpack_bf16x2(wu.w); wf[6] = t.x; wf[7] = t.y;
-      t = unpack_bf16x2(bu.x); bfv[0] = t.x; bfv[1] = t.y; t = unpack_bf16x2(bu.y); bfv[2] = t.x; bfv[3] = t.y;
-      t = unpack_bf16x2(bu.z); bfv[4] = t.x; bfv[5] = t.y; t = unpack_bf16x2(bu.w); bfv[6] = t.x; bfv[7] = t.y;
-      float o[8];
+      float wf[8], bfv[8], o[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(w + vi * 8)), wf);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(b + vi * 8)), bfv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         o[j] = (v[i][j] - mean) * rstd * wf[j] + bfv[j];
@@ -73,44 +87,32 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const bf16* __restrict__
   }
 }
 
-// ------------------------------------------------------------------ RMSNorm (HF Llama semantics)
-// y = w * bf16( x * rsqrt(mean(x^2) + eps) )     (transformers/models/llama/modeling_llama.py:53-67)
-template <int MAX_V>
+// HF LlamaRMSNorm: y = w * bf16( x * rsqrt(mean(x^2) + eps) )     (transformers/models/llama/modeling_llama.py:53-67)
+template <int MAXV>
 __global__ void __launch_bounds__(128) rmsnorm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ w,
                                                       bf16* __restrict__ y, long long ldy, int rows, int cols, float eps) {
-  __shared__ float red[32];
-  const int row = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const bf16* xr = x + (long long)row * ldx;
   bf16* yr = y + (long long)row * ldy;
   const int nvec = cols >> 3;
-  float v[MAX_V][8];
+  float v[MAXV][8];
+  load_row<MAXV>(xr, nvec, lane, v);
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_V; ++i) {
-    int vi = threadIdx.x + i * 128;
-    if (vi < nvec) {
-      uint4 u = *reinterpret_cast<const uint4*>(xr + vi * 8);
-      float2 t;
-      t = unpack_bf16x2(u.x); v[i][0] = t.x; v[i][1] = t.y;
-      t = unpack_bf16x2(u.y); v[i][2] = t.x; v[i][3] = t.y;
-      t = unpack_bf16x2(u.z); v[i][4] = t.x; v[i][5] = t.y;
-      t = unpack_bf16x2(u.w); v[i][6] = t.x; v[i][7] = t.y;
+  for (int i = 0; i < MAXV; ++i)
+    if (lane + i * 32 < nvec) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) sq += v[i][j] * v[i][j];
     }
-  }
-  const float rstd = rsqrtf(block_sum(sq, red) / (float)cols + eps);
+  const float rstd = rsqrtf(warp_sum(sq) / (float)cols + eps);
 #pragma unroll
-  for (int i = 0; i < MAX_V; ++i) {
-    int vi = threadIdx.x + i * 128;
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + i * 32;
     if (vi < nvec) {
-      uint4 wu = __ldg(reinterpret_cast<const uint4*>(w + vi * 8));
-      float wf[8];
-      float2 t;
-      t = unpack_bf16x2(wu.x); wf[0] = t.x; wf[1] = t.y; t = unpack_bf16x2(wu.y); wf[2] = t.x; wf[3] = t.y;
-      t = unpack_bf16x2(wu.z); wf[4] = t.x; wf[5] = t.y; t = unpack_bf16x2(wu.w); wf[6] = t.x; wf[7] = t.y;
-      float o[8];
+      float wf[8], o[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(w + vi * 8)), wf);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = wf[j] * rbf(v[i][j] * rstd);
       uint4 ou;
@@ -351,10 +353,11 @@ extern "C" int vsb_layernorm_bf16(const void* x, long long ldx, const void* w, c
   VSB_CHECK_ARG(x && w && b && y, "vsb_layernorm_bf16: null pointer");
   VSB_CHECK_ARG(cols % 8 == 0 && cols <= 128 * 8 * 4 && ldx % 8 == 0 && ldy % 8 == 0, "vsb_layernorm_bf16: cols=%d must be a multiple of 8 and <= 4096", cols);
   if (rows <= 0) return VSB_OK;
+  const int blocks = (rows + 3) / 4;
   if (cols <= 1024)
-    layernorm_kernel<1><<<rows, 128, 0, STREAM(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (const bf16*)b, (bf16*)y, ldy, rows, cols, eps, act);
+    layernorm_kernel<4><<<blocks, 128, 0, STREAM(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (const bf16*)b, (bf16*)y, ldy, rows, cols, eps, act);
   else
-    layernorm_kernel<4><<<rows, 128, 0, STREAM(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (const bf16*)b, (bf16*)y, ldy, rows, cols, eps, act);
+    layernorm_kernel<16><<<blocks, 128, 0, STREAM(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (const bf16*)b, (bf16*)y, ldy, rows, cols, eps, act);
   VSB_LAUNCH_CHECK();
   return VSB_OK;
 }
@@ -364,10 +367,11 @@ extern "C" int vsb_rmsnorm_bf16(const void* x, long long ldx, const void* w, voi
   VSB_CHECK_ARG(x && w && y, "vsb_rmsnorm_bf16: null pointer");
   VSB_CHECK_ARG(cols % 8 == 0 && cols <= 128 * 8 * 4 && ldx % 8 == 0 && ldy % 8 == 0, "vsb_rmsnorm_bf16: cols=%d must be a multiple of 8 and <= 4096", cols);
   if (rows <= 0) return VSB_OK;
+  const int blocks = (rows + 3) / 4;
   if (cols <= 1024)
-    rmsnorm_kernel<1><<<rows, 128, 0, STREAM(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (bf16*)y, ldy, rows, cols, eps);
+    rmsnorm_kernel<4><<<blocks, 128, 0, STREAM(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (bf16*)y, ldy, rows, cols, eps);
   else
-    rmsnorm_kernel<4><<<rows, 128, 0, STREAM(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (bf16*)y, ldy, rows, cols, eps);
+    rmsnorm_kernel<16><<<blocks, 128, 0, STREAM(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (bf16*)y, ldy, rows, cols, eps);
   VSB_LAUNCH_CHECK();
   return VSB_OK;
 }
