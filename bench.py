@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="frontier batch (crops per engine call)")
     ap.add_argument("--tiny", action="store_true", help="tiny model (debug only; not a valid bench)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--attn-impl", type=int, default=0, help="A/B switch for vsb_attn_set_impl (0 = production dispatch)")
     return ap.parse_args()
 
 
@@ -234,6 +235,8 @@ def run_b200(args):
     from vstar_b200.visual_search import visual_search_many
     from vstar_b200.vsm import VSM
 
+    if args.attn_impl:
+        _lib.call("vsb_attn_set_impl", args.attn_impl)
     cfg = tiny_config() if args.tiny else VSMConfig()
     t0 = time.time()
     weights = VSMWeights(cfg, lambda n, _s=synth.state_dict_shapes(cfg): synth.synthetic_tensor(n, _s[n], seed=1234, device="cuda"))

@@ -210,12 +210,14 @@ def test_rope_bit_exact(ops):
     assert torch.equal(out2[:, :, 2], qkv.view(B, T, 3, H, D)[:, :, 2])
 
 
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1, 2, 3])
 @pytest.mark.parametrize("B,H,S,D,causal", [(1, 2, 257, 64, False), (2, 3, 2305, 64, False), (2, 4, 320, 128, True),
                                             (1, 2, 64, 128, True), (3, 2, 1, 128, False), (1, 1, 130, 64, True),
-                                            (2, 2, 128, 64, False), (1, 3, 384, 128, False), (2, 2, 515, 64, True)])
+                                            (2, 2, 128, 64, False), (1, 3, 384, 128, False), (2, 2, 515, 64, True), (1, 2, 577, 64, False),
+                                            (2, 1, 256, 64, True), (1, 2, 1000, 64, True)])
 def test_flash_attn(ops, B, H, S, D, causal, impl):
-    """impl 1 = mma.sync kernel, 2 = tcgen05 kernel (both behind vsb_flash_attn_bf16)"""
+    """impl 1 = mma.sync kernel, 2 = tcgen05 kernels (two-tile ping-pong kernel for head_dim 64, Sq > 128), 3 = tcgen05
+    single-tile kernel only (all behind vsb_flash_attn_bf16)"""
     from vstar_b200 import _lib
     qkv = rnd(B * S, 3 * H * D, seed=40)
     _lib.call("vsb_attn_set_impl", impl)

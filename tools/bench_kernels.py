@@ -56,7 +56,7 @@ def main():
         out = torch.empty(B * S, H * D, dtype=BF, device="cuda")
         fl = 4 * B * H * S * S * D * (0.5 if causal else 1.0)
         var = {}
-        for tag, impl in (("mma_sync", 1), ("tcgen05", 2)):
+        for tag, impl in (("mma_sync", 1), ("tcgen05", 2), ("tcgen05_1tile", 3)):
             _lib.call("vsb_attn_set_impl", impl)
             var[tag] = round(fl / timeit(lambda: ops.attn_fused_qkv(qkv, B, S, H, D, causal, D ** -0.5, out=out)) / 1e9, 1)
         _lib.call("vsb_attn_set_impl", 0)

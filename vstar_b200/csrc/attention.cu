@@ -318,8 +318,13 @@ __global__ void __launch_bounds__(128) attn_small_kernel(const bf16* __restrict_
 int vsb_flash_attn_tc(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_rs, long long k_bs, long long k_rs,
                       long long v_bs, long long v_rs, long long o_bs, long long o_rs, int B, int H, int Sq, int Sk, int D, int causal,
                       float scale, cudaStream_t stream);
-static int g_attn_impl = 0;   // 0 auto, 1 = mma.sync kernel, 2 = tcgen05 kernel
-extern "C" int vsb_attn_set_impl(int impl) { g_attn_impl = impl; return VSB_OK; }
+void vsb_attn_tc_set_variant(int v);
+static int g_attn_impl = 0;   // 0 auto, 1 = mma.sync kernel, 2 = tcgen05 kernel(s), 3 = tcgen05 single-tile kernel only
+extern "C" int vsb_attn_set_impl(int impl) {
+  g_attn_impl = (impl == 3) ? 2 : impl;
+  vsb_attn_tc_set_variant(impl == 3 ? 1 : 0);
+  return VSB_OK;
+}
 
 extern "C" int vsb_flash_attn_bf16(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_rs,
                                    long long k_bs, long long k_rs, long long v_bs, long long v_rs, long long o_bs,

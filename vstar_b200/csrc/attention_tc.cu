@@ -127,6 +127,17 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* v)
       "r"(v[30]), "r"(v[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32_x8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32_x8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 // one MUFU op: 2^x, |rel err| <= 2^-22, ex2(-inf) = 0
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -417,6 +428,259 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------- ping-pong variant (head_dim 64): two Q tiles per CTA
+// One CTA owns 256 queries = tiles A and B of one (batch, head) and streams K/V once for both.  Softmax group A (8 warps)
+// and group B (8 warps) work on different tiles, so while one group is in its TMEM-read / MUFU phase the tensor core
+// serves the other group's S = QK^T and O += PV, and the two groups' TMEM-read and MUFU phases interleave instead of
+// running back-to-back (the single-tile kernel above is bound by exactly that serialisation: XU 46 %, tensor 22 % in ncu).
+//   TMEM: S^A @0, S^B @128, O^A @256, O^B @320.  smem: Q 2x16K, K/V ring 3x32K, P^A, P^B 32K each, row-max scratch.
+// A thread owns half a score row (64 keys): row r = 32*(warp%4) + lane of its group's tile, column half (warp-4)%8/4.
+struct ASmem2 {
+  static constexpr int KV_ST = 3;
+  static constexpr int Q_BYTES = 2 * SUB_BYTES;                    // tiles A, B (128 x 64 each)
+  static constexpr int KV_STAGE_BYTES = 2 * SUB_BYTES;             // K then V
+  static constexpr int P_BYTES = 2 * SUB_BYTES;                    // 128 x 128 bf16 per group
+  static constexpr int P_OFF = Q_BYTES + KV_ST * KV_STAGE_BYTES;
+  static constexpr int RED_OFF = P_OFF + 2 * P_BYTES;
+  static constexpr int RED_BYTES = 2 * 2 * 2 * 128 * 4;            // [group][parity][half][row]
+  static constexpr int BAR_OFF = RED_OFF + RED_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 128;
+};
+
+__global__ void __launch_bounds__(640, 1)
+attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                const AttnTcParams p) {
+  using L = ASmem2;
+  constexpr int D = 64;
+  constexpr int ST = L::KV_ST;
+  constexpr uint32_t TMEM_COLS = 512;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + L::Q_BYTES;
+  uint8_t* sP = smem + L::P_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;                 // [ST]
+  uint64_t* kv_empty = kv_full + ST;            // [ST]
+  uint64_t* s_full = kv_empty + ST;             // [2] per group
+  uint64_t* p_full = s_full + 2;                // [2] per group: 8 warp arrivals
+  uint64_t* pv_done = p_full + 2;               // [2] per group
+  uint64_t* s_free = pv_done + 2;               // [2] per group: 8 warp arrivals (S^g is in registers, its TMEM columns are free)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_free + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int off = p.Sk - p.Sq;
+  const bool tileB = (q0 + 128) < p.Sq;         // second tile has at least one valid row (CTA-uniform)
+  int nblk = (p.Sk + BKV - 1) / BKV;
+  if (p.causal) {
+    int last_key = q0 + 255 + off;
+    if (last_key > p.Sk - 1) last_key = p.Sk - 1;
+    if (last_key < 0) last_key = 0;
+    const int nb = last_key / BKV + 1;
+    if (nb < nblk) nblk = nb;
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < ST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], tileB ? 2 : 1); }   // one commit per MMA issuer
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_full[g], 8);
+      mbar_init(&pv_done[g], 1);
+      mbar_init(&s_free[g], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer
+      mbar_arrive_expect_tx(q_full, L::Q_BYTES);
+      tma_load_3d(sQ, &tmQ, p.q_col0 + h * D, q0, b, q_full);
+      tma_load_3d(sQ + SUB_BYTES, &tmQ, p.q_col0 + h * D, q0 + 128, b, q_full);     // rows >= Sq arrive as zeros
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        uint8_t* dst = sKV + stage * L::KV_STAGE_BYTES;
+        mbar_arrive_expect_tx(&kv_full[stage], L::KV_STAGE_BYTES);
+        tma_load_3d(dst, &tmK, p.k_col0 + h * D, j * BKV, b, &kv_full[stage]);
+        tma_load_3d(dst + SUB_BYTES, &tmV, p.v_col0 + h * D, j * BKV, b, &kv_full[stage]);
+        if (++stage == ST) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 || (warp == 3 && tileB)) {
+    if (lane == 0) {
+      // ---------------- MMA issuer of tile g (warp 1: tile A, warp 3: tile B).  S^g_{j+1} is issued as soon as the softmax
+      // group has pulled S^g_j into registers (s_free), i.e. while it is still exponentiating block j, so the group never
+      // waits for the tensor core; PV^g_j follows when P^g_j is in shared memory.  The two issuers interleave freely.
+      const int g = warp >> 1;
+      constexpr uint32_t idesc_s = make_idesc(128, BKV, 0);
+      constexpr uint32_t idesc_o = make_idesc(128, D, 1);
+      const uint32_t aQ = smem_u32(sQ) + g * SUB_BYTES, aP = smem_u32(sP) + g * L::P_BYTES;
+      auto issue_S = [&](int stage) {
+        const uint32_t aK = smem_u32(sKV + stage * L::KV_STAGE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_f16(tmem_base + g * 128, desc_kmajor(aQ + kk * 32), desc_kmajor(aK + kk * 32), idesc_s, kk > 0 ? 1u : 0u);
+        umma_commit(&s_full[g]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_S(0);
+      int vs = 0, ks = 1 % ST;
+      uint32_t kph = (ST == 1) ? 1 : 0;
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) {
+          mbar_wait(&kv_full[ks], kph);
+          mbar_wait(&s_free[g], j & 1);
+          tc_fence_after();
+          issue_S(ks);
+        }
+        mbar_wait(&p_full[g], j & 1);
+        tc_fence_after();
+        const uint32_t aV = smem_u32(sKV + vs * L::KV_STAGE_BYTES + SUB_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk)
+          umma_f16(tmem_base + 256 + g * 64, desc_kmajor(aP + (kk >> 2) * SUB_BYTES + (kk & 3) * 32), desc_mnmajor(aV + kk * 2048), idesc_o,
+                   (j > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&pv_done[g]);
+        umma_commit(&kv_empty[vs]);                 // this tile is done with K_j / V_j
+        if (++vs == ST) vs = 0;
+        if (++ks == ST) { ks = 0; kph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int g = (warp - 4) >> 3;                // softmax group == Q tile
+    if (g == 0 || tileB) {
+      const int qtr = warp & 3;
+      const int half = ((warp - 4) & 7) >> 2;     // key-column half of the block
+      const int r = qtr * 32 + lane;
+      const int qrow = q0 + g * 128 + r;
+      const uint32_t lane_addr = (uint32_t)(qtr * 32) << 16;
+      const uint32_t tS = tmem_base + lane_addr + (uint32_t)(g * 128 + half * 64);
+      const uint32_t tO = tmem_base + lane_addr + (uint32_t)(256 + g * 64 + half * 32);
+      float* red = reinterpret_cast<float*>(smem + L::RED_OFF) + g * 512;       // [parity][half][row]
+      const int bar_id = 1 + g * 4 + qtr;                                        // the 2 warps sharing these rows
+      float m_ref = 0.f, l_part = 0.f;
+      const int kmax = p.causal ? min(qrow + off, p.Sk - 1) : (p.Sk - 1);
+
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(&s_full[g], j & 1);
+        tc_fence_after();
+        uint32_t v[64];
+        tmem_ld_32x32(tS, v);
+        tmem_ld_32x32(tS + 32, v + 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[g]);
+        const int nvis = kmax - (j * BKV + half * 64) + 1;
+        float mx = -INFINITY;
+        if (nvis >= 64) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            if (i >= nvis) v[i] = 0xff800000u;
+            mx = fmaxf(mx, __uint_as_float(v[i]));
+          }
+        }
+        mx *= p.scale_log2;
+        float* rj = red + (j & 1) * 256;
+        rj[half * 128 + r] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        mx = fmaxf(rj[r], rj[128 + r]);
+        float corr = 1.f;
+        if (j == 0) {
+          m_ref = (mx == -INFINITY) ? 0.f : mx;
+        } else if (mx > m_ref + 8.f) {
+          corr = exp2f(m_ref - mx);
+          m_ref = mx;
+        }
+        // P^g (single buffer) is free and O^g holds blocks < j once P_{j-1} V_{j-1} has retired
+        if (j >= 1) { mbar_wait(&pv_done[g], (j - 1) & 1); tc_fence_after(); }
+        if (__any_sync(0xffffffffu, corr != 1.f)) {
+          // rare (lazy rescale): 8 columns at a time so the 64 live score registers are not spilled around this branch
+#pragma unroll 1
+          for (int c = 0; c < 32; c += 8) {
+            uint32_t ov[8];
+            tmem_ld_32x32_x8(tO + c, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
+            tmem_st_32x32_x8(tO + c, ov);
+          }
+          tmem_st_wait();
+          l_part *= corr;
+        }
+        uint8_t* sub = sP + g * L::P_BYTES + half * SUB_BYTES + r * 128;
+        float ls = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(v[ch * 8 + 2 * i]), p.scale_log2, -m_ref));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(v[ch * 8 + 2 * i + 1]), p.scale_log2, -m_ref));
+            ls += p0 + p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+          *reinterpret_cast<uint4*>(sub + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        l_part += ls;
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g]);
+      }
+      // ---- epilogue
+      float* rl = red + (nblk & 1) * 256;
+      rl[half * 128 + r] = l_part;
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      const float l_run = rl[r] + rl[128 + r];
+      const int jl = nblk - 1;
+      mbar_wait(&pv_done[g], jl & 1);
+      tc_fence_after();
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      uint32_t ov[32];
+      tmem_ld_32x32(tO, ov);
+      tmem_ld_wait();
+      if (qrow < p.Sq) {
+        bf16* dst = p.o + (long long)b * p.o_bs + (long long)qrow * p.o_rs + (long long)h * D + half * 32;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(ov[8 * i + 0]) * inv, __uint_as_float(ov[8 * i + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(ov[8 * i + 2]) * inv, __uint_as_float(ov[8 * i + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(ov[8 * i + 4]) * inv, __uint_as_float(ov[8 * i + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(ov[8 * i + 6]) * inv, __uint_as_float(ov[8 * i + 7]) * inv);
+          reinterpret_cast<uint4*>(dst)[i] = w;
+        }
+      }
+      tc_fence_before();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 // ---------------------------------------------------------------- host
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -464,6 +728,9 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, 
 
 }  // namespace
 
+static int g_tc_variant = 0;    // 0 auto (two-tile ping-pong kernel for head_dim 64), 1 = single-tile kernel only
+void vsb_attn_tc_set_variant(int v) { g_tc_variant = v; }
+
 // same contract as vsb_flash_attn_bf16 (called by it for the shapes this kernel covers)
 int vsb_flash_attn_tc(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_rs, long long k_bs, long long k_rs,
                       long long v_bs, long long v_rs, long long o_bs, long long o_rs, int B, int H, int Sq, int Sk, int D, int causal,
@@ -481,6 +748,14 @@ int vsb_flash_attn_tc(const void* q, const void* k, const void* v, void* o, long
   p.H = H; p.Sq = Sq; p.Sk = Sk; p.causal = causal;
   p.q_col0 = p.k_col0 = p.v_col0 = 0;
   p.scale_log2 = scale * 1.4426950408889634f;
+  if (D == 64 && g_tc_variant != 1 && Sq > 128) {
+    static bool set2 = false;
+    if (!set2) { VSB_CUDA(cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ASmem2::TOTAL)); set2 = true; }
+    dim3 grid((Sq + 255) / 256, H, B);
+    attn_tc2_kernel<<<grid, 640, ASmem2::TOTAL, stream>>>(tq, tk, tv, p);
+    VSB_LAUNCH_CHECK();
+    return VSB_OK;
+  }
   if (D == 64) return launch<64>(tq, tk, tv, p, B, stream);
   return launch<128>(tq, tk, tv, p, B, stream);
 }
