@@ -358,7 +358,34 @@ def case_vqa(tag, img_seed):
                             option_losses=ref_losses.numpy(), gen=np.array(gen))
 
 
+def case_bench_eval():
+    """the reference's own eval_model (vstar_bench_eval.py:168-273) over a tiny synthetic benchmark tree, with the stub VQA /
+    stub VSM injected in place of the two model classes; its output JSON is the golden for vstar_b200.bench_eval."""
+    print("[golden] bench_eval")
+    import tempfile
+    import types
+    import vstar_bench_eval as E   # the reference module
+    from tests.helpers import StubVQA, make_bench_folder
+    with tempfile.TemporaryDirectory() as tmp:
+        folder = make_bench_folder(os.path.join(tmp, "bench"))
+        out = os.path.join(tmp, "out.json")
+        E.VQA_LLM = lambda args: StubVQA()
+        E.VSM = lambda args: StubVSM()
+        E.eval_model(types.SimpleNamespace(benchmark_folder=folder, output_path=out, vsm_model_path="stub", minimum_size_scale=4.0,
+                                           minimum_size=224))
+        res = json.load(open(out))
+    for t in res:
+        res[t] = sorted(res[t], key=lambda r: r["image"])       # os.listdir order is file-system dependent
+    with open(os.path.join(GOLDEN_DIR, "bench_eval_golden.json"), "w") as f:
+        json.dump(res, f, indent=1)
+    print("   ", {t: len(v) for t, v in res.items()}, "samples;", sum(len(r["search_result"]) for v in res.values() for r in v), "search results")
+
+
 def main():
+    if os.environ.get("GOLDEN_ONLY") == "bench_eval":
+        assert ref_shims.reference_available()
+        ref_shims.install(*hf_cfgs(O.tiny_config()))
+        return case_bench_eval()
     assert ref_shims.reference_available(), "needs /root/reference (build container only)"
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(8)
@@ -377,6 +404,7 @@ def main():
     case_search_model(m, sd, cfg, "a", img_seed=31, w=640, h=512, smallest=200, confidence_high=2.0,
                       target_cue_threshold=-1e9, target_cue_threshold_minimum=-1e9)
     case_vqa("a", img_seed=41)
+    case_bench_eval()
     print("golden vectors written to", GOLDEN_DIR)
 
 

@@ -66,3 +66,57 @@ class StubVSM:
 def synth_image(seed, w, h):
     from PIL import Image
     return Image.fromarray(np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8), "RGB")
+
+
+# ---------------------------------------------------------------- V*Bench driver fixtures (tests/test_bench_eval.py)
+MISSING_MSG = ("Sorry, I can not answer the question. Some visual information about the following objects is missing or "
+               "unclear:")
+
+
+class _Proc:
+    image_mean = [0.48145466, 0.4578275, 0.40821073]
+
+
+class StubVQA:
+    """Deterministic stand-in for VQA_LLM (vstar_bench_eval.py:49-165): answers are pure functions of their arguments, so the
+    option an implementation picks checks every string / box it fed in (focus message, normalised boxes, long/short flags)."""
+    image_processor = _Proc()
+
+    def __init__(self):
+        self.log = []
+
+    def free_form_inference(self, image, question, max_new_tokens=512):
+        import zlib
+        k = zlib.crc32(question.encode()) % 3
+        self.log.append(("free", image.size, question))
+        if k == 0:
+            return "It is blue."
+        if k == 1:
+            return MISSING_MSG + " the red mug."
+        return MISSING_MSG + " a dog, the blue umbrella, traffic light."
+
+    def get_object_crop(self, image, bbox, patch_scale=1.0):
+        return torch.tensor([round(float(v), 2) for v in bbox] + [patch_scale], dtype=torch.float32)
+
+    def multiple_choices_inference(self, image, question, options, object_crops=None, images_long=None, objects_long=None):
+        import zlib
+        key = repr((image.size, question, options, None if object_crops is None else object_crops.round().tolist(),
+                    images_long, objects_long))
+        self.log.append(("choice", key))
+        return zlib.crc32(key.encode()) % len(options)
+
+
+def make_bench_folder(root):
+    """tiny synthetic V*Bench tree: <root>/{direct_attributes,relative_position}/{name}.jpg|.png + {name}.json"""
+    import json
+    import os
+    spec = {"direct_attributes": [("sa_1", 31, 640, 400), ("sa_2", 32, 300, 520), ("sa_3", 33, 512, 512), ("sa_4", 34, 700, 260)],
+            "relative_position": [("sa_5", 35, 480, 360), ("sa_6", 36, 256, 600), ("sa_7", 37, 900, 300)]}
+    for test_type, items in spec.items():
+        d = os.path.join(root, test_type)
+        os.makedirs(d, exist_ok=True)
+        for name, seed, w, h in items:
+            synth_image(seed, w, h).save(os.path.join(d, name + ".png"))
+            with open(os.path.join(d, name + ".json"), "w") as f:
+                json.dump({"question": f"What is the colour of item {seed}?", "options": ["red", "blue", "green", "white"][:2 + seed % 3]}, f)
+    return root

@@ -53,6 +53,42 @@ def focus_question(question, object_names, norm_boxes):
     return msg + "\n" + question
 
 
+def smallest_size_for(image, minimum_size_scale=4.0, minimum_size=224):
+    """vstar_bench_eval.py:210"""
+    return max(int(np.ceil(min(image.width, image.height) / minimum_size_scale)), minimum_size)
+
+
+def collect_search_results(missing, results):
+    """vstar_bench_eval.py:212-225: boxes of the final patch shifted to image coordinates, one entry per found instance"""
+    search_result = []
+    for name, (final_step, _path_length, _ok, all_valid) in zip(missing, results):
+        patch = final_step["bbox"]
+        boxes = all_valid if all_valid is not None else [final_step["detection_result"]]
+        for b in boxes:
+            b = b.clone()
+            b[0] += patch[0]
+            b[1] += patch[1]
+            search_result.append({"bbox": b.tolist(), "name": name})
+    return search_result
+
+
+def choose_option(vqa_llm, image, question, options, missing, search_result):
+    """vstar_bench_eval.py:226-257: option scoring, with the searched objects spliced in as <object> features"""
+    if not missing:
+        # the reference scores the options on the re-opened, UNPADDED image here (vstar_bench_eval.py:227, :257)
+        return vqa_llm.multiple_choices_inference(image, question, options)
+    bg = tuple(int(x * 255) for x in vqa_llm.image_processor.image_mean)
+    padded, left, top = expand2square_center(image, bg)
+    names = [r["name"] for r in search_result]
+    boxes = deepcopy([r["bbox"] for r in search_result])
+    objects_long = [True] * len(names) if len(names) <= 2 else [False] * len(names)
+    crops = torch.stack([vqa_llm.get_object_crop(image, b, patch_scale=1.2) for b in boxes], 0)
+    shifted = [[b[0] + left, b[1] + top, b[2], b[3]] for b in boxes]
+    nboxes = [normalize_bbox(b, padded.width, padded.height) for b in shifted]
+    return vqa_llm.multiple_choices_inference(padded, focus_question(question, names, nboxes), options, crops,
+                                              images_long=[False], objects_long=objects_long)
+
+
 def seal_answer(vqa_llm, vsm, image, question, options, minimum_size_scale=4.0, minimum_size=224, search_batch=16,
                 prediction_override=None, search_kwargs=None):
     """-> dict with the reference's per-sample result keys (question, options, prediction_freeform, missing_objects,
@@ -63,28 +99,10 @@ def seal_answer(vqa_llm, vsm, image, question, options, minimum_size_scale=4.0, 
     missing = parse_missing_objects(prediction)
     search_result = []
     if missing:
-        smallest = max(int(np.ceil(min(image.width, image.height) / minimum_size_scale)), minimum_size)
+        smallest = smallest_size_for(image, minimum_size_scale, minimum_size)
         jobs = [(image, name, smallest) for name in missing]
         results, _ = visual_search_many(vsm, jobs, batch_size=search_batch, **(search_kwargs or {}))
-        for name, (final_step, path_length, ok, all_valid) in zip(missing, results):
-            patch = final_step["bbox"]
-            boxes = all_valid if all_valid is not None else [final_step["detection_result"]]
-            for b in boxes:
-                b = b.clone()
-                b[0] += patch[0]
-                b[1] += patch[1]
-                search_result.append({"bbox": b.tolist(), "name": name})
-    if missing:
-        names = [r["name"] for r in search_result]
-        boxes = deepcopy([r["bbox"] for r in search_result])
-        objects_long = [True] * len(names) if len(names) <= 2 else [False] * len(names)
-        crops = torch.stack([vqa_llm.get_object_crop(image, b, patch_scale=1.2) for b in boxes], 0)
-        padded, left, top = expand2square_center(image, bg)
-        shifted = [[b[0] + left, b[1] + top, b[2], b[3]] for b in boxes]
-        nboxes = [normalize_bbox(b, padded.width, padded.height) for b in shifted]
-        chosen = vqa_llm.multiple_choices_inference(padded, focus_question(question, names, nboxes), options, crops,
-                                                    images_long=[False], objects_long=objects_long)
-    else:
-        chosen = vqa_llm.multiple_choices_inference(padded, question, options)
+        search_result = collect_search_results(missing, results)
+    chosen = choose_option(vqa_llm, image, question, options, missing, search_result)
     return dict(question=question, options=options, prediction_freeform=prediction, missing_objects=missing,
                 search_result=search_result, option_chosen=chosen, correct=1 if chosen == 0 else 0)
