@@ -40,7 +40,11 @@ int vsb_version(void);
 int vsb_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
                   const void* bias, const void* residual, long long ldr, int epilogue, int out_fp32, int rows_per_group,
                   long long group_stride, long long group_offset, void* stream);
-/* testing / tuning hooks: force the kernel variant (64/128/256 = single-CTA tile width, 512 = 2-CTA cta_group::2
+/* CUDA-event profiling of every vsb_gemm_bf16 launch (bench.py's roofline leg): begin clears the record; end synchronises
+ * and returns the summed algorithmic flops (2*M*N*K), the summed event durations in ms and the launch count. */
+int vsb_gemm_profile_begin(void);
+int vsb_gemm_profile_end(double* flops, double* ms, long long* launches);
+/* testing / tuning hooks: force the kernel variant (1 = CUDA-core skinny kernel for M <= 8, 64/128/256 = single-CTA tile width, 512 = 2-CTA cta_group::2
  * 256x256 cluster tiles, 0 = auto) and the CTA count (0 = #SMs); tile-rasterisation band height in m-blocks (0 = auto) */
 int vsb_gemm_set_tuning(int force_bn, int max_ctas);
 int vsb_gemm_set_group_m(int group_m);
@@ -75,6 +79,22 @@ int vsb_argmax_rows_f32(const void* x, long long ld, int rows, int n, void* idx_
  * (CrossEntropyLoss, /root/reference/vstar_bench_eval.py:154-159) */
 int vsb_nll_rows_f32(const void* logits, long long ld, int rows, int n, const void* labels_i64, void* out_f32, void* stream);
 int vsb_copy2d_b16(const void* src, long long lds, void* dst, long long ldd, long long rows, int cols, void* stream);
+
+/* The whole Llama decoder stack over Tn new rows per sequence, in place on the residual stream x [B*Tn, d] bf16
+ * (HF LlamaModel layers as called from llava_llama.py:93-105 / llava_search_llama.py:80-92).  Fused q|k|v rows live in
+ * cache [n_layers][Bc][Tmax][3d] at positions past..past+Tn; weights: wqkv [3d,d] (q|k|v rows), wo [d,d], wgu [2*inter,d]
+ * with gate/up rows interleaved, wdown [d,inter], ln1/ln2 [d]; rope tables bf16 [max_pos, head_dim/2]; scratch: bf16
+ * B*Tn*(2d+inter) elements.  8 kernel launches per layer. */
+typedef struct {
+  const void* ln1;
+  const void* wqkv;
+  const void* wo;
+  const void* ln2;
+  const void* wgu;
+  const void* wdown;
+} vsb_llama_layer_t;
+int vsb_llama_layers(const vsb_llama_layer_t* layers, int n_layers, void* x, int B, int Tn, int past, void* cache, int Bc, int Tmax,
+                     int d, int H, int inter, float rms_eps, const void* rope_cos, const void* rope_sin, void* scratch, void* stream);
 
 /* softmax(QK^T*scale [+causal]) V, head_dim 64/128; element (b,s,h,d) at base + b*bs + s*rs + h*D + d.
  * HF CLIP/OWL attention (modeling_clip.py:261-329) and Llama attention (modeling_llama.py:199-221). */

@@ -176,24 +176,7 @@ def get_patch(bbox, image_width, image_height, patch_size=224, patch_scale=None)
 
 
 def vqa_state_dict_shapes(cfg: VSMConfig):
-    """tensors of seal_vqa_7b that the path reads (reference key layout)"""
+    """tensors of seal_vqa_7b that the path reads (reference key layout); the table itself lives with the synthetic-weight
+    helpers (vstar_b200/synth.py) so tools can build a random-init model without importing the oracle"""
     from vstar_b200 import synth
-    s = {k: v for k, v in synth.state_dict_shapes(cfg).items()
-         if k.startswith("model.layers.") or k.startswith("model.vision_tower.") or k in
-         ("model.embed_tokens.weight", "model.norm.weight", "lm_head.weight", "model.mm_projector.weight", "model.mm_projector.bias")}
-    C, d = cfg.clip_hidden, cfg.hidden
-    p = "model.mm_projector_object."
-    s[p + "0.weight"] = (C,); s[p + "0.bias"] = (C,)
-    s[p + "1.latents"] = (32, C); s[p + "1.media_pos_emb"] = (1, 1, C)
-    inner = 16 * 96
-    for i in range(6):
-        a = f"{p}1.layers.{i}.0."
-        for n in ("norm_media", "norm_latents"):
-            s[a + n + ".weight"] = (C,); s[a + n + ".bias"] = (C,)
-        s[a + "to_q.weight"] = (inner, C); s[a + "to_kv.weight"] = (2 * inner, C); s[a + "to_out.weight"] = (C, inner)
-        f = f"{p}1.layers.{i}.1."
-        s[f + "0.weight"] = (C,); s[f + "0.bias"] = (C,)
-        s[f + "1.weight"] = (4 * C, C); s[f + "3.weight"] = (C, 4 * C)
-    s[p + "1.norm.weight"] = (C,); s[p + "1.norm.bias"] = (C,)
-    s[p + "2.weight"] = (d, C); s[p + "2.bias"] = (d,)
-    return s
+    return synth.vqa_state_dict_shapes(cfg)

@@ -164,6 +164,77 @@ def test_gemm_row_remap_and_strided(ops):
     assert float(o2[:, :N].abs().max()) == 0
 
 
+@pytest.mark.parametrize("D,causal,Sq,Sk", [(64, False, 1, 2305), (64, True, 4, 130), (128, False, 2, 700)])
+def test_attn_decode_kernel_shapes(ops, D, causal, Sq, Sk):
+    from vstar_b200 import _lib
+    B, H = 2, 3
+    q, k, v = rnd(B * Sq, H * D, seed=44), rnd(B * Sk, H * D, seed=45), rnd(B * Sk, H * D, seed=46)
+    out = torch.empty(B * Sq, H * D, dtype=BF, device="cuda")
+    _lib.call("vsb_attn_set_impl", 4)
+    try:
+        ops.flash_attn(q, k, v, out, B, H, Sq, Sk, D, causal, D ** -0.5, Sq * H * D, H * D, Sk * H * D, H * D, Sk * H * D, H * D, Sq * H * D, H * D)
+        torch.cuda.synchronize()
+    finally:
+        _lib.call("vsb_attn_set_impl", 0)
+    qf, kf, vf = [t.view(B, -1, H, D).transpose(1, 2).float() for t in (q, k, v)]
+    att = qf @ kf.transpose(-1, -2) * D ** -0.5
+    if causal:
+        att = att.masked_fill(~torch.ones(Sq, Sk, device="cuda").tril(Sk - Sq).bool(), float("-inf"))
+    ref = (torch.softmax(att, -1) @ vf).transpose(1, 2).reshape(B * Sq, H * D)
+    assert torch.allclose(out.float(), ref, rtol=2e-2, atol=2e-2), rel_err(out, ref)
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 4096, 4096), (1, 1001, 1000), (2, 514, 768), (3, 77, 11008), (4, 2048, 264), (5, 333, 2048),
+                                   (8, 12288, 1024), (7, 32004, 512)])
+def test_gemm_skinny(ops, M, N, K):
+    """decode-sized problems (M <= 2 in production, up to 8 when forced) take the CUDA-core weight-streaming kernel
+    (gemm_skinny.cu); it must agree with the
+    fp32 reference AND with the tcgen05 kernel on every epilogue variant (same semantics behind vsb_gemm_bf16)"""
+    from vstar_b200 import _lib
+    a, w, b = rnd(M, K, seed=61), rnd(N, K, scale=1 / math.sqrt(K), seed=62), rnd(N, seed=63)
+    r, r32 = rnd(M, N, seed=64), torch.randn(M, N, device="cuda")
+
+    def run_all():
+        o = [ops.gemm(a, w, out_dtype=torch.float32), ops.gemm(a, w, bias=b, residual=r, epilogue=ops.EPI_QUICK_GELU),
+             ops.gemm(a, w, bias=b, epilogue=ops.EPI_GELU), ops.gemm(a, w, residual=r, epilogue=ops.EPI_RELU),
+             ops.gemm(a, w, bias=b, residual=r32, out_dtype=torch.float32)]
+        if N % 2 == 0:
+            o.append(ops.gemm(a, w, epilogue=ops.EPI_SWIGLU))
+        return o
+
+    _lib.call("vsb_gemm_set_tuning", 1, 0)            # force the skinny kernel (errors out if it cannot take the shape)
+    try:
+        sk = run_all()
+        _lib.call("vsb_gemm_set_tuning", 64, 0)       # tcgen05 single-CTA kernel
+        tc = run_all()
+    finally:
+        _lib.call("vsb_gemm_set_tuning", 0, 0)
+    auto = ops.gemm(a, w, out_dtype=torch.float32)
+    assert torch.equal(auto, sk[0] if M <= 2 else tc[0]) or M > 2      # production dispatch = skinny kernel for M <= 2
+    y = a.float() @ w.float().t()
+    yb = y + b.float()
+    refs = [y, yb * torch.sigmoid(1.702 * yb) + r.float(), F.gelu(yb), F.relu(y) + r.float(), yb + r32]
+    if N % 2 == 0:
+        refs.append(F.silu(y[:, 0::2]) * y[:, 1::2])
+    for i, (s_, t_, ref) in enumerate(zip(sk, tc, refs)):
+        tol = dict(rtol=1e-4, atol=1e-3) if s_.dtype == torch.float32 else dict(rtol=1e-2, atol=3e-2)
+        assert s_.shape == ref.shape and torch.allclose(s_.float(), ref, **tol), (i, rel_err(s_, ref))
+        assert torch.allclose(s_.float(), t_.float(), **tol), (i, rel_err(s_, t_))
+
+
+def test_gemm_skinny_row_remap_strided(ops):
+    """decode writes its q|k|v row into the fused cache through the row remap; A / C are strided views"""
+    B, K, N, T, p0 = 3, 512, 384, 40, 17
+    a_wide, w, b = rnd(B, 2 * K, seed=65), rnd(N, K, scale=1 / math.sqrt(K), seed=66), rnd(N, seed=67)
+    buf = torch.zeros(B * T, 2 * N, dtype=BF, device="cuda")
+    ops.gemm(a_wide[:, K:], w, out=buf[:, N:], bias=b, rows_per_group=1, group_stride=T, group_offset=p0)
+    ref = a_wide[:, K:].float() @ w.float().t() + b.float()
+    got = buf.view(B, T, 2 * N)
+    assert torch.allclose(got[:, p0, N:].float(), ref, rtol=1e-2, atol=2e-2)
+    got[:, p0, N:] = 0
+    assert float(got.abs().max()) == 0
+
+
 def test_layernorm_rmsnorm(ops):
     for rows, cols in [(7, 64), (300, 768), (257, 1024), (33, 4096), (10, 256)]:
         x, w, b = rnd(rows, cols, seed=20), (1 + 0.1 * torch.randn(cols)).to(BF).cuda(), rnd(cols, scale=0.1, seed=21)
@@ -234,10 +305,11 @@ def test_flash_attn(ops, B, H, S, D, causal, impl):
     assert torch.allclose(out.float(), ref, rtol=2e-2, atol=2e-2), rel_err(out, ref)
 
 
-@pytest.mark.parametrize("impl,Sq,Sk", [(1, 3, 100), (2, 3, 100), (2, 70, 300), (1, 70, 300)])
+@pytest.mark.parametrize("impl,Sq,Sk", [(1, 3, 100), (2, 3, 100), (2, 70, 300), (1, 70, 300), (4, 1, 100), (4, 3, 100), (4, 4, 383),
+                                        (0, 1, 377), (4, 2, 9)])
 def test_flash_attn_kv_cache_decode(ops, impl, Sq, Sk):
     """Sq < Sk with causal offset (decode / chunked prefill against a KV cache with a different row stride; cache rows
-    beyond Sk hold NaNs and must never be read into the result)"""
+    beyond Sk hold NaNs and must never be read into the result); impl 4 = split-KV cluster decode kernel (auto for Sq <= 4)"""
     from vstar_b200 import _lib
     B, H, D, Tmax = 2, 4, 128, 384
     q = rnd(B * Sq, H * D, seed=41)
@@ -382,3 +454,51 @@ def test_ops_fail_loudly_on_cpu_tensors(ops):
     from vstar_b200._lib import VsbError
     with pytest.raises(VsbError):
         ops.gemm(torch.zeros(8, 8, dtype=BF), torch.zeros(8, 8, dtype=BF))
+
+
+def test_llama_layers_native_runner(ops):
+    """vsb_llama_layers (one native call for the whole stack) == the same kernels sequenced from Python, bit for bit,
+    for a prefill (Tn = 70) followed by a decode step (Tn = 1, skinny GEMMs) on the fused-QKV cache"""
+    d, H, inter, nl, B, Tmax = 256, 2, 512, 3, 2, 96
+    hd = d // H
+    layers = [dict(ln1=(1 + 0.1 * torch.randn(d)).to(BF).cuda(), wqkv=rnd(3 * d, d, scale=d ** -0.5, seed=70 + i),
+                   wo=rnd(d, d, scale=d ** -0.5, seed=80 + i), ln2=(1 + 0.1 * torch.randn(d)).to(BF).cuda(),
+                   wgu=rnd(2 * inter, d, scale=d ** -0.5, seed=90 + i), wdown=rnd(d, inter, scale=inter ** -0.5, seed=100 + i))
+              for i in range(nl)]
+    cos_t, sin_t = _rope_tables(Tmax, hd)
+    table = ops.llama_layer_table(layers)
+
+    def python_stack(x, cache, Tn, past):
+        ld = 3 * d
+        attn = torch.empty((B * Tn, d), dtype=BF, device="cuda")
+        for li, L in enumerate(layers):
+            h = ops.rmsnorm(x, L["ln1"], 1e-6)
+            cl = cache[li].view(B * Tmax, ld)
+            ops.gemm(h, L["wqkv"], out=cl, rows_per_group=Tn, group_stride=Tmax, group_offset=past)
+            ops.rope_(cl, Tn, H, hd, cos_t, sin_t, pos0=past, rows=B * Tn, group_stride=Tmax, group_offset=past)
+            ops.flash_attn(cl[past:], cl[:, d:], cl[:, 2 * d:], attn, B, H, Tn, past + Tn, hd, True, hd ** -0.5, Tmax * ld, ld, Tmax * ld, ld,
+                           Tmax * ld, ld, Tn * d, d)
+            ops.gemm(attn, L["wo"], out=x, residual=x)
+            h = ops.rmsnorm(x, L["ln2"], 1e-6)
+            gu = ops.gemm(h, L["wgu"], epilogue=ops.EPI_SWIGLU)
+            ops.gemm(gu, L["wdown"], out=x, residual=x)
+        return x
+
+    def native_stack(x, cache, Tn, past):
+        scratch = torch.empty(B * Tn * (2 * d + inter), dtype=BF, device="cuda")
+        return ops.llama_layers(table, nl, x, B, Tn, past, cache, B, Tmax, d, H, inter, 1e-6, cos_t, sin_t, scratch)
+
+    outs = []
+    for fn in (python_stack, native_stack):
+        cache = torch.zeros(nl, B, Tmax, 3 * d, dtype=BF, device="cuda")
+        x0 = rnd(B * 70, d, seed=110).clone()
+        y0 = fn(x0, cache, 70, 0).clone()
+        x1 = rnd(B * 1, d, seed=111).clone()
+        y1 = fn(x1, cache, 1, 70).clone()
+        outs.append((y0, y1, cache.clone()))
+    torch.cuda.synchronize()
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    assert float(outs[0][0].float().abs().max()) > 0 and torch.isfinite(outs[0][1].float()).all()
+    with pytest.raises(Exception):
+        native_stack(rnd(B * 30, d, seed=112), torch.zeros(nl, B, Tmax, 3 * d, dtype=BF, device="cuda"), 30, 70)    # exceeds Tmax

@@ -17,6 +17,8 @@ c_f = ctypes.c_float
 # name -> argtypes (must match include/vstar_b200.h)
 SIGNATURES = {
     "vsb_gemm_bf16": [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_p, c_p, c_ll, c_i, c_i, c_i, c_ll, c_ll, c_p],
+    "vsb_gemm_profile_begin": [],
+    "vsb_gemm_profile_end": [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_ll)],
     "vsb_gemm_set_tuning": [c_i, c_i],
     "vsb_gemm_set_group_m": [c_i],
     "vsb_layernorm_bf16": [c_p, c_ll, c_p, c_p, c_p, c_ll, c_i, c_i, c_f, c_i, c_p],
@@ -32,6 +34,7 @@ SIGNATURES = {
     "vsb_nll_rows_f32": [c_p, c_ll, c_i, c_i, c_p, c_p, c_p],
     "vsb_argmax_rows_f32": [c_p, c_ll, c_i, c_i, c_p, c_p, c_p],
     "vsb_copy2d_b16": [c_p, c_ll, c_p, c_ll, c_ll, c_i, c_p],
+    "vsb_llama_layers": [c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p],
     "vsb_flash_attn_bf16": [c_p, c_p, c_p, c_p, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
     "vsb_attn_set_impl": [c_i],
     "vsb_attn_small_bf16": [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
@@ -45,6 +48,13 @@ SIGNATURES = {
     "vsb_resample_h_u8": [c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p],
     "vsb_resample_v_u8": [c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p, ctypes.POINTER(c_f), ctypes.POINTER(c_f), c_p],
 }
+
+
+
+class LlamaLayer(ctypes.Structure):
+    """vsb_llama_layer_t"""
+    _fields_ = [("ln1", c_p), ("wqkv", c_p), ("wo", c_p), ("ln2", c_p), ("wgu", c_p), ("wdown", c_p)]
+
 
 _lib = None
 

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libvstar_b200.so")
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "elementwise.cu", "heads.cu", "image.cu"]
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "gemm_skinny.cu", "llama_layers.cu", "attention.cu", "attention_tc.cu", "elementwise.cu", "heads.cu", "image.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include"), "-I", CSRC]

@@ -318,8 +318,174 @@ __global__ void __launch_bounds__(128) attn_small_kernel(const bf16* __restrict_
 int vsb_flash_attn_tc(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_rs, long long k_bs, long long k_rs,
                       long long v_bs, long long v_rs, long long o_bs, long long o_rs, int B, int H, int Sq, int Sk, int D, int causal,
                       float scale, cudaStream_t stream);
+
+// ------------------------------------------------------------------ decode attention (Sq <= 4 new rows against a long KV cache)
+// HBM/latency-bound: one (batch, head) reads Sk rows of K and V once.  The FA2-style kernel above gives such a problem ONE
+// CTA per head (32 CTAs for Vicuna-7B, 22 us per layer at Sk = 700).  Here the keys of a head are split over a CLUSTER of 8
+// CTAs (flash-decoding); each warp streams its keys with the row spread over the 32 lanes (coalesced 128/256 B rows, 4 keys
+// in flight per warp), keeps an online-softmax partial (m, l, acc) per query, warps combine through shared memory, and
+// cluster rank 0 combines the 8 CTA partials through DISTRIBUTED shared memory - no global scratch, no second kernel.
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+constexpr int DEC_SPLITS = 8;     // cluster size
+constexpr int DEC_WARPS = 4;
+constexpr int DEC_MAXQ = 4;
+constexpr int DEC_U = 4;          // keys in flight per warp
+
+template <int D>
+__global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_kernel(const AttnParams p) {
+  constexpr int EPL = D / 32;                                   // elements per lane
+  cg::cluster_group cluster = cg::this_cluster();
+  const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ float s_m[DEC_WARPS][DEC_MAXQ], s_l[DEC_WARPS][DEC_MAXQ];
+  __shared__ float s_acc[DEC_WARPS][DEC_MAXQ][D];
+  __shared__ float c_m[DEC_MAXQ], c_l[DEC_MAXQ];                // this CTA's combined partial (read remotely by rank 0)
+  __shared__ float c_acc[DEC_MAXQ][D];
+
+  const int off = p.Sk - p.Sq;
+  const int chunk = (p.Sk + DEC_SPLITS - 1) / DEC_SPLITS;
+  const int k_begin = split * chunk;
+  const int k_end = min(p.Sk, k_begin + chunk);
+  const bf16* qb = p.q + (long long)b * p.q_bs + (long long)h * D + lane * EPL;
+  const bf16* kb = p.k + (long long)b * p.k_bs + (long long)h * D + lane * EPL;
+  const bf16* vb = p.v + (long long)b * p.v_bs + (long long)h * D + lane * EPL;
+
+  float q[DEC_MAXQ][EPL], acc[DEC_MAXQ][EPL], m[DEC_MAXQ], l[DEC_MAXQ];
+#pragma unroll
+  for (int qi = 0; qi < DEC_MAXQ; ++qi) {
+    m[qi] = -INFINITY;
+    l[qi] = 0.f;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      acc[qi][e] = 0.f;
+      q[qi][e] = (qi < p.Sq) ? bf2f(qb[(long long)qi * p.q_rs + e]) * p.scale_log2 : 0.f;
+    }
+  }
+
+  for (int j0 = k_begin + warp; j0 < k_end; j0 += DEC_WARPS * DEC_U) {
+    float kf[DEC_U][EPL], vf[DEC_U][EPL];
+#pragma unroll
+    for (int u = 0; u < DEC_U; ++u) {
+      const int j = j0 + u * DEC_WARPS;
+      if (j < k_end) {
+        if (EPL == 4) {
+          const uint2 kr = *reinterpret_cast<const uint2*>(kb + (long long)j * p.k_rs);
+          const uint2 vr = *reinterpret_cast<const uint2*>(vb + (long long)j * p.v_rs);
+          float2 t;
+          t = unpack_bf16x2(kr.x); kf[u][0] = t.x; kf[u][1] = t.y;
+          t = unpack_bf16x2(kr.y); kf[u][2 % EPL] = t.x; kf[u][3 % EPL] = t.y;
+          t = unpack_bf16x2(vr.x); vf[u][0] = t.x; vf[u][1] = t.y;
+          t = unpack_bf16x2(vr.y); vf[u][2 % EPL] = t.x; vf[u][3 % EPL] = t.y;
+        } else {
+          const uint32_t kr = *reinterpret_cast<const uint32_t*>(kb + (long long)j * p.k_rs);
+          const uint32_t vr = *reinterpret_cast<const uint32_t*>(vb + (long long)j * p.v_rs);
+          float2 t;
+          t = unpack_bf16x2(kr); kf[u][0] = t.x; kf[u][1] = t.y;
+          t = unpack_bf16x2(vr); vf[u][0] = t.x; vf[u][1] = t.y;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) kf[u][e] = vf[u][e] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int qi = 0; qi < DEC_MAXQ; ++qi) {
+      if (qi < p.Sq) {                                          // warp-uniform
+        const int jmax = p.causal ? qi + off : p.Sk - 1;
+        float sc[DEC_U];
+        float mx = m[qi];
+#pragma unroll
+        for (int u = 0; u < DEC_U; ++u) {
+          float d = 0.f;
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) d = fmaf(q[qi][e], kf[u][e], d);
+          d = warp_sum(d);
+          const int j = j0 + u * DEC_WARPS;
+          sc[u] = (j < k_end && j <= jmax) ? d : -INFINITY;
+          mx = fmaxf(mx, sc[u]);
+        }
+        if (mx != -INFINITY) {
+          const float corr = exp2f(m[qi] - mx);                 // m = -inf on first use -> 0
+          m[qi] = mx;
+          float ls = 0.f;
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) acc[qi][e] *= corr;
+#pragma unroll
+          for (int u = 0; u < DEC_U; ++u) {
+            const float pr = exp2f(sc[u] - mx);
+            ls += pr;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) acc[qi][e] = fmaf(pr, vf[u][e], acc[qi][e]);
+          }
+          l[qi] = l[qi] * corr + ls;
+        }
+      }
+    }
+  }
+  // warps -> CTA partial
+#pragma unroll
+  for (int qi = 0; qi < DEC_MAXQ; ++qi) {
+    if (lane == 0) { s_m[warp][qi] = m[qi]; s_l[warp][qi] = l[qi]; }
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) s_acc[warp][qi][lane * EPL + e] = acc[qi][e];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < DEC_MAXQ * D; idx += DEC_WARPS * 32) {
+    const int qi = idx / D, d = idx - qi * D;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < DEC_WARPS; ++w) M = fmaxf(M, s_m[w][qi]);
+    float a = 0.f, ll = 0.f;
+#pragma unroll
+    for (int w = 0; w < DEC_WARPS; ++w) {
+      const float f = (s_m[w][qi] == -INFINITY) ? 0.f : exp2f(s_m[w][qi] - M);
+      a += s_acc[w][qi][d] * f;
+      ll += s_l[w][qi] * f;
+    }
+    c_acc[qi][d] = a;
+    if (d == 0) { c_m[qi] = M; c_l[qi] = ll; }
+  }
+  cluster.sync();
+  if (cluster.block_rank() == 0) {
+    for (int idx = threadIdx.x; idx < p.Sq * D; idx += DEC_WARPS * 32) {
+      const int qi = idx / D, d = idx - qi * D;
+      float M = -INFINITY;
+      for (int r = 0; r < DEC_SPLITS; ++r) M = fmaxf(M, *cluster.map_shared_rank(&c_m[qi], r));
+      float a = 0.f, ll = 0.f;
+      for (int r = 0; r < DEC_SPLITS; ++r) {
+        const float mr = *cluster.map_shared_rank(&c_m[qi], r);
+        const float f = (mr == -INFINITY) ? 0.f : exp2f(mr - M);
+        a += *cluster.map_shared_rank(&c_acc[qi][d], r) * f;
+        ll += *cluster.map_shared_rank(&c_l[qi], r) * f;
+      }
+      p.o[(long long)b * p.o_bs + (long long)qi * p.o_rs + (long long)h * D + d] = f2bf(ll > 0.f ? a / ll : 0.f);
+    }
+  }
+  cluster.sync();                                               // peers' shared memory must outlive rank 0's reads
+}
+
+template <int D>
+static int launch_decode(const AttnParams& p, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(DEC_SPLITS, p.H, p.B);
+  cfg.blockDim = dim3(DEC_WARPS * 32);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = DEC_SPLITS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VSB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_kernel<D>, p));
+  return VSB_OK;
+}
+
 void vsb_attn_tc_set_variant(int v);
-static int g_attn_impl = 0;   // 0 auto, 1 = mma.sync kernel, 2 = tcgen05 kernel(s), 3 = tcgen05 single-tile kernel only
+static int g_attn_impl = 0;   // 0 auto, 1 = mma.sync kernel, 2 = tcgen05 kernel(s), 3 = tcgen05 single-tile kernel only, 4 = decode kernel
 extern "C" int vsb_attn_set_impl(int impl) {
   g_attn_impl = (impl == 3) ? 2 : impl;
   vsb_attn_tc_set_variant(impl == 3 ? 1 : 0);
@@ -337,6 +503,15 @@ extern "C" int vsb_flash_attn_bf16(const void* q, const void* k, const void* v, 
                 "vsb_flash_attn_bf16: strides must be multiples of 8 elements (16 B)");
   VSB_CHECK_ARG(((uintptr_t)q & 15) == 0 && ((uintptr_t)k & 15) == 0 && ((uintptr_t)v & 15) == 0 && ((uintptr_t)o & 15) == 0,
                 "vsb_flash_attn_bf16: pointers must be 16-byte aligned");
+  if (g_attn_impl == 4 || (g_attn_impl == 0 && Sq <= DEC_MAXQ && Sk >= 64)) {
+    VSB_CHECK_ARG(Sq <= DEC_MAXQ, "vsb_flash_attn_bf16: decode kernel forced but Sq=%d > %d", Sq, DEC_MAXQ);
+    AttnParams pd;
+    pd.q = (const bf16*)q; pd.k = (const bf16*)k; pd.v = (const bf16*)v; pd.o = (bf16*)o;
+    pd.q_bs = q_bs; pd.q_rs = q_rs; pd.k_bs = k_bs; pd.k_rs = k_rs; pd.v_bs = v_bs; pd.v_rs = v_rs; pd.o_bs = o_bs; pd.o_rs = o_rs;
+    pd.B = B; pd.H = H; pd.Sq = Sq; pd.Sk = Sk; pd.causal = causal;
+    pd.scale_log2 = scale * 1.4426950408889634f;
+    return D == 64 ? launch_decode<64>(pd, reinterpret_cast<cudaStream_t>(stream)) : launch_decode<128>(pd, reinterpret_cast<cudaStream_t>(stream));
+  }
   if (g_attn_impl == 2 || (g_attn_impl == 0 && Sq >= 64))
     return vsb_flash_attn_tc(q, k, v, o, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, B, H, Sq, Sk, D, causal, scale,
                              reinterpret_cast<cudaStream_t>(stream));

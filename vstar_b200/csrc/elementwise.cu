@@ -122,6 +122,42 @@ __global__ void __launch_bounds__(128) rmsnorm_kernel(const bf16* __restrict__ x
   }
 }
 
+// few rows (decode): one 256-thread block per row so the row's loads are all in flight at once; a single warp per row
+// (above) serialises 16 dependent-latency loads and measured 11 us for one 4096-wide row.  Same arithmetic, same rounding.
+__global__ void __launch_bounds__(256) rmsnorm_row_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ w,
+                                                          bf16* __restrict__ y, long long ldy, int cols, float eps) {
+  __shared__ float red[32];
+  const bf16* xr = x + (long long)blockIdx.x * ldx;
+  bf16* yr = y + (long long)blockIdx.x * ldy;
+  const int nvec = cols >> 3;
+  constexpr int MAXV = 4;                      // cols <= 8192
+  float v[MAXV][8], wf[MAXV][8];
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = threadIdx.x + i * 256;
+    if (vi < nvec) {
+      unpack8(*reinterpret_cast<const uint4*>(xr + vi * 8), v[i]);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(w + vi * 8)), wf[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sq += v[i][j] * v[i][j];
+    }
+  }
+  const float rstd = rsqrtf(block_sum(sq, red) / (float)cols + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = threadIdx.x + i * 256;
+    if (vi < nvec) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = wf[i][j] * rbf(v[i][j] * rstd);
+      uint4 ou;
+      ou.x = pack_bf16x2(o[0], o[1]); ou.y = pack_bf16x2(o[2], o[3]); ou.z = pack_bf16x2(o[4], o[5]); ou.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(yr + vi * 8) = ou;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ RoPE (rotate-half), in place on q and k
 // x' = bf16( bf16(x*cos) + bf16(rot(x)*sin) ); cos/sin come from host-built bf16 tables [max_pos, D/2]
 // (built with the same fp32 torch ops as HF: transformers/models/llama/modeling_llama.py:117-168),
@@ -368,6 +404,11 @@ extern "C" int vsb_rmsnorm_bf16(const void* x, long long ldx, const void* w, voi
   VSB_CHECK_ARG(cols % 8 == 0 && cols <= 128 * 8 * 4 && ldx % 8 == 0 && ldy % 8 == 0, "vsb_rmsnorm_bf16: cols=%d must be a multiple of 8 and <= 4096", cols);
   if (rows <= 0) return VSB_OK;
   const int blocks = (rows + 3) / 4;
+  if (rows <= 32 && cols >= 2048 && cols <= 8192) {
+    rmsnorm_row_kernel<<<rows, 256, 0, STREAM(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (bf16*)y, ldy, cols, eps);
+    VSB_LAUNCH_CHECK();
+    return VSB_OK;
+  }
   if (cols <= 1024)
     rmsnorm_kernel<4><<<blocks, 128, 0, STREAM(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (bf16*)y, ldy, rows, cols, eps);
   else

@@ -892,7 +892,69 @@ extern "C" int vsb_gemm_set_group_m(int group_m) {
   return VSB_OK;
 }
 
+int vsb_gemm_skinny_launch(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
+                           const void* bias, const void* residual, long long ldr, int epilogue, int out_fp32, int rows_per_group,
+                           long long group_stride, long long group_offset, cudaStream_t stream);
+
+// ---------------------------------------------------------------- CUDA-event profiling of every launch (bench.py roofline leg)
+#include <vector>
+namespace {
+struct ProfRec { cudaEvent_t a, b; double flops; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+void prof_clear() {
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+}
+}  // namespace
+
+extern "C" int vsb_gemm_profile_begin(void) {
+  prof_clear();
+  g_prof_on = true;
+  return VSB_OK;
+}
+extern "C" int vsb_gemm_profile_end(double* flops, double* ms, long long* launches) {
+  g_prof_on = false;
+  VSB_CUDA(cudaDeviceSynchronize());
+  double f = 0, t = 0;
+  for (auto& r : g_prof) {
+    float e = 0.f;
+    VSB_CUDA(cudaEventElapsedTime(&e, r.a, r.b));
+    f += r.flops;
+    t += e;
+  }
+  if (flops) *flops = f;
+  if (ms) *ms = t;
+  if (launches) *launches = (long long)g_prof.size();
+  prof_clear();
+  return VSB_OK;
+}
+
+static int gemm_dispatch(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
+                         const void* bias, const void* residual, long long ldr, int epilogue, int out_fp32, int rows_per_group,
+                         long long group_stride, long long group_offset, void* stream_);
+
 extern "C" int vsb_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M,
+                             int N, int K, const void* bias, const void* residual, long long ldr, int epilogue,
+                             int out_fp32, int rows_per_group, long long group_stride, long long group_offset,
+                             void* stream_) {
+  if (!g_prof_on)
+    return gemm_dispatch(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, epilogue, out_fp32, rows_per_group, group_stride,
+                         group_offset, stream_);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ProfRec r;
+  VSB_CUDA(cudaEventCreate(&r.a));
+  VSB_CUDA(cudaEventCreate(&r.b));
+  r.flops = 2.0 * (double)M * (double)N * (double)K;
+  VSB_CUDA(cudaEventRecord(r.a, stream));
+  const int rc = gemm_dispatch(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, epilogue, out_fp32, rows_per_group, group_stride,
+                               group_offset, stream_);
+  VSB_CUDA(cudaEventRecord(r.b, stream));
+  g_prof.push_back(r);
+  return rc;
+}
+
+static int gemm_dispatch(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M,
                              int N, int K, const void* bias, const void* residual, long long ldr, int epilogue,
                              int out_fp32, int rows_per_group, long long group_stride, long long group_offset,
                              void* stream_) {
@@ -923,6 +985,13 @@ extern "C" int vsb_gemm_bf16(const void* A, long long lda, const void* W, long l
   p.group_stride = group_stride;
   p.group_offset = group_offset;
 
+  // decode-sized problems are HBM-bound on W: CUDA-core streaming kernel (gemm_skinny.cu); force_bn = 1 forces it (tests)
+  // measured (tools/bench_vqa.py, CUDA-graph timing): 0.57-0.95 of the HBM roofline at M = 1, ahead of the tcgen05 tiles up to
+  // M = 2; from M = 3 the CUDA-core FMAs/unpacks bind and the tensor-core kernel (0.63-0.76 at M = 16) wins
+  if (((g_force_bn == 0 && M <= 2) || (g_force_bn == 1 && M <= 8)) && (K % 8) == 0)
+    return vsb_gemm_skinny_launch(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, epilogue, out_fp32, rows_per_group, group_stride,
+                                  group_offset, stream);
+  VSB_CHECK_ARG(g_force_bn != 1, "vsb_gemm_bf16: skinny kernel forced but M=%d > 8 or K %% 8 != 0", M);
   const int sms = g_max_ctas > 0 ? g_max_ctas : vsb_num_sms();
   // tile-width choice: minimise (waves * BN) ~ time; prefer the wider tile on ties (less A re-streaming)
   int bn = 64;

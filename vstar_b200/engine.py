@@ -198,6 +198,7 @@ class LlamaClipCore:
         self.max_tokens = max_tokens
         self._cache = None
         self._cache_shape = None
+        self._layer_table = None        # ctypes array of per-layer weight pointers for the native layer runner
         self.stats = dict(verified=0, fallback=0)
 
     # ------------------------------------------------------------------ ViT
@@ -248,28 +249,16 @@ class LlamaClipCore:
 
     def _llm_layers(self, x, B, Tn, past, Tmax):
         """Run all decoder layers over the Tn new rows per sequence in x [B*Tn, d] (in place on the residual stream).
-        Fused q|k|v rows live in the per-layer cache [B, Tmax, 3d] at positions past..past+Tn."""
+        Fused q|k|v rows live in the per-layer cache [B, Tmax, 3d] at positions past..past+Tn.  One native call
+        (csrc/llama_layers.cu) sequences the 8 kernels of every layer: RMSNorm, QKV GEMM writing cache rows, RoPE in
+        place, attention through strides, o-proj + residual, RMSNorm, gate|up GEMM with SwiGLU epilogue, down + residual."""
         c = self.cfg
-        d, H, hd = c.hidden, c.n_heads, c.head_dim
-        cache = self._cache
+        if self._layer_table is None:
+            self._layer_table = ops.llama_layer_table(self.w.layers)
         Bc, Tm = self._cache_shape[1], self._cache_shape[2]
-        ld = 3 * d
-        scale = hd ** -0.5
-        attn_out = torch.empty((B * Tn, d), dtype=BF, device=self.dev)
-        for li, L in enumerate(self.w.layers):
-            h = ops.rmsnorm(x, L["ln1"], c.rms_eps)
-            cl = cache[li].view(Bc * Tm, ld)
-            ops.gemm(h, L["wqkv"], out=cl, rows_per_group=Tn, group_stride=Tm, group_offset=past)
-            ops.rope_(cl, Tn, H, hd, self.w.rope_cos, self.w.rope_sin, pos0=past, rows=B * Tn, group_stride=Tm, group_offset=past)
-            q = cl[past:]                    # element offset past*ld, batch stride Tm*ld
-            k = cl[:, d:]
-            v = cl[:, 2 * d:]
-            ops.flash_attn(q, k, v, attn_out, B, H, Tn, past + Tn, hd, True, scale, Tm * ld, ld, Tm * ld, ld, Tm * ld, ld, Tn * d, d)
-            ops.gemm(attn_out, L["wo"], out=x, residual=x)
-            h = ops.rmsnorm(x, L["ln2"], c.rms_eps)
-            gu = ops.gemm(h, L["wgu"], epilogue=ops.EPI_SWIGLU)
-            ops.gemm(gu, L["wdown"], out=x, residual=x)
-        return x
+        scratch = torch.empty((B * Tn * (2 * c.hidden + c.intermediate),), dtype=BF, device=self.dev)
+        return ops.llama_layers(self._layer_table, len(self.w.layers), x, B, Tn, past, self._cache, Bc, Tm, c.hidden, c.n_heads,
+                                c.intermediate, c.rms_eps, self.w.rope_cos, self.w.rope_sin, scratch)
 
     def _logits_rows(self, x, rows):
         """final RMSNorm + lm_head on selected rows of the residual stream -> (hidden [n,d], argmax [n], logits fp32 [n,V])"""

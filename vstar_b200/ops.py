@@ -36,20 +36,40 @@ def _rows2d(t):
 
 
 # optional per-launch profiling of the dominant kernel (bench.py roofline): CUDA events around every GEMM launch
-_prof = None
-
-
 def profile_begin():
-    global _prof
-    _prof = []
+    """CUDA events around every vsb_gemm_bf16 launch from here on (recorded inside the library, so launches issued by the native
+    layer runner are covered too)"""
+    call("vsb_gemm_profile_begin")
 
 
 def profile_end():
     """-> (total algorithmic flops, total ms, launches) over the GEMM launches since profile_begin()"""
-    global _prof
-    rec, _prof = _prof, None
-    torch.cuda.synchronize()
-    return sum(r[0] for r in rec), sum(r[1].elapsed_time(r[2]) for r in rec), len(rec)
+    import ctypes
+    f, t, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+    call("vsb_gemm_profile_end", ctypes.byref(f), ctypes.byref(t), ctypes.byref(n))
+    return f.value, t.value, n.value
+
+
+def llama_layer_table(layers):
+    """layers: list of dicts with ln1, wqkv, wo, ln2, wgu, wdown tensors (kept alive by the caller) -> ctypes array"""
+    arr = (_lib.LlamaLayer * len(layers))()
+    for i, L in enumerate(layers):
+        for k in ("ln1", "wqkv", "wo", "ln2", "wgu", "wdown"):
+            t = L[k]
+            assert t.dtype == BF16 and t.is_contiguous() and t.is_cuda, k
+            setattr(arr[i], k, t.data_ptr())
+    return arr
+
+
+def llama_layers(table, n_layers, x, B, Tn, past, cache, Bc, Tmax, d, H, inter, eps, rope_cos, rope_sin, scratch):
+    """whole decoder stack in ONE native call (csrc/llama_layers.cu): in place on x [B*Tn, d]"""
+    _chk(x, BF16), _chk(cache, BF16), _chk(scratch, BF16)
+    assert x.is_contiguous() and cache.is_contiguous() and x.shape == (B * Tn, d)
+    assert scratch.numel() >= B * Tn * (2 * d + inter)
+    _lib.launches += 8 * n_layers
+    call("vsb_llama_layers", table, n_layers, x.data_ptr(), B, Tn, past, cache.data_ptr(), Bc, Tmax, d, H, inter, float(eps),
+         rope_cos.data_ptr(), rope_sin.data_ptr(), scratch.data_ptr(), _stream())
+    return x
 
 
 def gemm(a, w, out=None, bias=None, residual=None, epilogue=EPI_NONE, out_dtype=BF16, rows_per_group=0,
@@ -71,15 +91,9 @@ def gemm(a, w, out=None, bias=None, residual=None, epilogue=EPI_NONE, out_dtype=
         _chk(bias, BF16)
         assert bias.numel() == N and bias.is_contiguous()
     _lib.launches += 1
-    if _prof is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
     call("vsb_gemm_bf16", pa, lda, pw, ldw, out.data_ptr(), out.stride(0), M, N, K, _p(bias), _p(residual),
          residual.stride(0) if residual is not None else 0, epilogue, out_fp32, rows_per_group, group_stride, group_offset,
          _stream())
-    if _prof is not None:
-        e1.record()
-        _prof.append((2.0 * M * N * K, e0, e1))
     return out
 
 
