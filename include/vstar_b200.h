@@ -84,7 +84,9 @@ int vsb_copy2d_b16(const void* src, long long lds, void* dst, long long ldd, lon
  * (HF LlamaModel layers as called from llava_llama.py:93-105 / llava_search_llama.py:80-92).  Fused q|k|v rows live in
  * cache [n_layers][Bc][Tmax][3d] at positions past..past+Tn; weights: wqkv [3d,d] (q|k|v rows), wo [d,d], wgu [2*inter,d]
  * with gate/up rows interleaved, wdown [d,inter], ln1/ln2 [d]; rope tables bf16 [max_pos, head_dim/2]; scratch: bf16
- * B*Tn*(2d+inter) elements.  8 kernel launches per layer. */
+ * B*Tn*(2d+inter) elements.  Ragged batches (continuous-batched decode): sequences are LEFT-padded in the cache so that
+ * they all end at row past+Tn; positions int32 [B*Tn] gives each new row its RoPE position and k_start int32 [B] the first
+ * cache row of each sequence (requires Tn <= 4); both NULL for the aligned case.  8 kernel launches per layer. */
 typedef struct {
   const void* ln1;
   const void* wqkv;
@@ -94,14 +96,23 @@ typedef struct {
   const void* wdown;
 } vsb_llama_layer_t;
 int vsb_llama_layers(const vsb_llama_layer_t* layers, int n_layers, void* x, int B, int Tn, int past, void* cache, int Bc, int Tmax,
-                     int d, int H, int inter, float rms_eps, const void* rope_cos, const void* rope_sin, void* scratch, void* stream);
+                     int d, int H, int inter, float rms_eps, const void* rope_cos, const void* rope_sin, const void* positions,
+                     const void* k_start, void* scratch, void* stream);
 
 /* softmax(QK^T*scale [+causal]) V, head_dim 64/128; element (b,s,h,d) at base + b*bs + s*rs + h*D + d.
  * HF CLIP/OWL attention (modeling_clip.py:261-329) and Llama attention (modeling_llama.py:199-221). */
 int vsb_flash_attn_bf16(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_rs, long long k_bs,
                         long long k_rs, long long v_bs, long long v_rs, long long o_bs, long long o_rs, int B, int H, int Sq, int Sk,
                         int D, int causal, float scale, void* stream);
-/* testing hook: 0 = auto (tcgen05 kernel for Sq >= 64, mma.sync kernel for decode-sized Sq), 1 = mma.sync, 2 = tcgen05 */
+/* Decode attention (Sq <= 4 new rows against a long KV cache; HF Llama attention with past_key_values as driven by
+ * generate(use_cache=True), /root/reference/vstar_bench_eval.py:91-103, :127-152): the keys of a head are split over a
+ * cluster of 8 CTAs and combined through distributed shared memory.  k_start: optional int32 [B], first valid key of each
+ * batch entry (left-padded ragged batches); NULL = 0.  vsb_flash_attn_bf16 routes Sq <= 4 here. */
+int vsb_attn_decode_bf16(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_rs, long long k_bs,
+                         long long k_rs, long long v_bs, long long v_rs, long long o_bs, long long o_rs, int B, int H, int Sq, int Sk,
+                         int D, int causal, float scale, const void* k_start, void* stream);
+/* testing hook: 0 = auto (tcgen05 kernels for Sq >= 64, split-KV decode kernel for Sq <= 4, mma.sync kernel between),
+ * 1 = mma.sync, 2 = tcgen05, 3 = tcgen05 single-tile kernel only, 4 = decode kernel */
 int vsb_attn_set_impl(int impl);
 /* SAM two-way transformer attention, head_dim 16/32 (segment_anything/modeling/transformer.py:220-242)
  * and SEAL perceiver-resampler attention, head_dim 96 (LLaVA/llava/model/multimodal_projector/perceiver.py:25-77). */

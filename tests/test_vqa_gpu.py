@@ -134,3 +134,58 @@ def test_full_seal_loop_tiny(setup):
     assert res["option_chosen"] in (0, 1, 2, 3) and all(len(r["bbox"]) == 4 for r in res["search_result"])
     res2 = seal_answer(vqa, vsm, img, "q", ["a", "b"], prediction_override="It is red.")
     assert res2["missing_objects"] == [] and res2["option_chosen"] in (0, 1)
+
+
+def test_continuous_batched_decode_matches_single_sequence(setup):
+    """ragged left-padded batch (prefill_ragged / decode_ragged / generate_batch) against the single-sequence path and the
+    fp32 oracle: per-step logits agree within the bf16 error scale, and every token generate_batch emits is a (near-)argmax
+    of the oracle along its own path"""
+    V, O, cfg, sd, eng = setup
+    rng = np.random.default_rng(5)
+    gen = torch.Generator().manual_seed(7)
+    reqs, embeds32 = [], []
+    for n_pre, n_post, long_ in ((5, 9, True), (12, 30, False), (3, 4, True)):
+        ids = [1] + rng.integers(3, cfg.vocab - 30, n_pre).tolist() + [-200] + rng.integers(3, cfg.vocab - 30, n_post).tolist()
+        image = torch.randn(1, 3, 224, 224, generator=gen)
+        reqs.append((ids, image.to(BF).cuda(), None, [long_], None))
+        embeds32.append(V.build_embeds(sd, cfg, torch.tensor([ids]), image, None, [long_], None))
+    lens_expected = [e.shape[1] for e in embeds32]
+    # single-sequence reference run (same engine): first-step logits and 3 teacher-forced decode steps
+    forced = [[7, 11, 13], [17, 19, 23], [29, 31, 37]]
+    single = []
+    for (ids, img, _, il, _), f in zip(reqs, forced):
+        x = eng.build_embeds(ids, img, None, il, None)
+        T = x.shape[0]
+        eng.prefill_embeds(x)
+        rows = [eng.last_logits(x)[0].clone()]
+        for s_, t in enumerate(f):
+            rows.append(eng.append_tokens([t], T + s_)[0].clone())
+        single.append(torch.stack(rows))
+    xs = [eng.build_embeds(ids, img, None, il, None) for ids, img, _, il, _ in reqs]
+    logits, Tpad, lens = eng.prefill_ragged(xs)
+    assert lens == lens_expected and Tpad == max(lens)
+    batch_rows = [logits.clone()]
+    for s_ in range(3):
+        batch_rows.append(eng.decode_ragged([f[s_] for f in forced], lens, Tpad, s_).clone())
+    emb = sd["model.embed_tokens.weight"]
+    for b in range(3):
+        got = torch.stack([r[b] for r in batch_rows])
+        e = embeds32[b].clone()
+        for s_ in range(4):
+            ref = V.forward_logits(sd, cfg, e)[0, -1]
+            assert rel(got[s_], ref) < 3e-2 and rel(single[b][s_], ref) < 3e-2, (b, s_, rel(got[s_], ref))
+            assert rel(got[s_], single[b][s_]) < 3e-2
+            if s_ < 3:
+                e = torch.cat([e, emb[torch.tensor([forced[b][s_]])].unsqueeze(0)], dim=1)
+    outs = eng.generate_batch(reqs, max_new_tokens=4, eos_token_id=-1)
+    assert [len(o) for o in outs] == [4, 4, 4]
+    for b in range(3):
+        e = embeds32[b].clone()
+        for t in outs[b]:
+            last = V.forward_logits(sd, cfg, e)[0, -1]
+            assert float(last.max() - last[t]) < 3e-2
+            e = torch.cat([e, emb[torch.tensor([t])].unsqueeze(0)], dim=1)
+    # a sequence that stops early idles while the others continue
+    first = outs[0][0]
+    outs2 = eng.generate_batch(reqs, max_new_tokens=4, eos_token_id=first)
+    assert outs2[0] == [first] and len(outs2[1]) >= 1

@@ -89,6 +89,16 @@ def main():
         g, wl = ev_time(lambda: eng.option_losses(q, opts, image, crops, il, ol), iters=3, warmup=1)
         res["vqa_options"] = dict(T=T, options=4, gpu_ms=g, wall_ms=wl)
         print(res["vqa_options"], flush=True)
+        for nb in (4, 8, 16):
+            reqs = []
+            for i in range(nb):
+                qi = [1] + rng.integers(1000, 30000, 30 + 3 * i).tolist() + [-200] + rng.integers(1000, 30000, 20 + 5 * i).tolist()
+                reqs.append((qi, image, None, [True], None))
+            g, wl = ev_time(lambda: eng.generate_batch(reqs, max_new_tokens=n_new, eos_token_id=-1), iters=2, warmup=1)
+            g1, wl1 = ev_time(lambda: eng.prefill_ragged([eng.build_embeds(*r) for r in reqs]), iters=2, warmup=1)
+            res[f"vqa_generate_batch{nb}"] = dict(B=nb, new_tokens=n_new, wall_ms=wl, prefill_wall_ms=wl1, ms_per_step=(wl - wl1) / n_new,
+                                                  tokens_per_s=nb * n_new / ((wl - wl1) / 1e3))
+            print(res[f"vqa_generate_batch{nb}"], flush=True)
         del eng, w
         torch.cuda.empty_cache()
     if which in ("all", "round"):

@@ -7,7 +7,8 @@ output JSON (keys question, options, image, prediction_freeform, missing_objects
 
 What changes is the schedule.  The reference answers one image at a time and runs the searches of that image one after
 another (vstar_bench_eval.py:208-211), so the VSM sees batch 1.  Here `images_in_flight` images are taken together:
-  1. free-form answers for the chunk (-> missing objects),
+  1. free-form answers for the chunk in ONE continuous-batched greedy decode (`VQA_LLM.free_form_inference_batch`: ragged
+     left-padded KV cache, every decode step reads the 7B weights once for all images) -> missing objects,
   2. ONE lock-step `visual_search_many` over every (image, missing object) of the chunk, so root and level-2 rounds, which
      cannot fill a GPU (let alone eight) on their own, share frontier batches (SURVEY.md §8e "scaling loss sources"),
   3. option scoring.
@@ -75,11 +76,16 @@ def eval_model(args, vqa_llm=None, vsm=None, log=print, search_kwargs=None):
             chunk = []
             for image_file, image_path, annotation_path in samples[c0:c0 + in_flight]:
                 image = Image.open(image_path).convert("RGB")
-                annotation = json.load(open(annotation_path))
-                padded, _, _ = expand2square_center(image, bg)
-                prediction = vqa_llm.free_form_inference(padded, annotation["question"])
-                chunk.append(dict(image_file=image_file, image=image, annotation=annotation, prediction=prediction,
-                                  missing=parse_missing_objects(prediction)))
+                chunk.append(dict(image_file=image_file, image=image, annotation=json.load(open(annotation_path))))
+            padded = [expand2square_center(smp["image"], bg)[0] for smp in chunk]
+            questions = [smp["annotation"]["question"] for smp in chunk]
+            if hasattr(vqa_llm, "free_form_inference_batch") and len(chunk) > 1:
+                predictions = vqa_llm.free_form_inference_batch(padded, questions)      # one continuous-batched decode
+            else:
+                predictions = [vqa_llm.free_form_inference(im, q) for im, q in zip(padded, questions)]
+            for smp, prediction in zip(chunk, predictions):
+                smp["prediction"] = prediction
+                smp["missing"] = parse_missing_objects(prediction)
             jobs, owner = [], []
             for i, smp in enumerate(chunk):
                 smallest = smallest_size_for(smp["image"], args.minimum_size_scale, args.minimum_size)

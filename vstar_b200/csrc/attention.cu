@@ -46,6 +46,7 @@ struct AttnParams {
   int B, H, Sq, Sk;
   int causal;      // query i attends keys j <= i + (Sk - Sq)
   float scale_log2;
+  const int* k_start = nullptr;   // decode kernel only: first valid key of each batch entry (left-padded ragged batches)
 };
 
 constexpr int FA_BN = 64;
@@ -345,8 +346,9 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_kernel(const AttnP
   __shared__ float c_acc[DEC_MAXQ][D];
 
   const int off = p.Sk - p.Sq;
-  const int chunk = (p.Sk + DEC_SPLITS - 1) / DEC_SPLITS;
-  const int k_begin = split * chunk;
+  const int k_first = p.k_start ? max(0, min(p.k_start[b], p.Sk)) : 0;
+  const int chunk = (p.Sk - k_first + DEC_SPLITS - 1) / DEC_SPLITS;
+  const int k_begin = k_first + split * chunk;
   const int k_end = min(p.Sk, k_begin + chunk);
   const bf16* qb = p.q + (long long)b * p.q_bs + (long long)h * D + lane * EPL;
   const bf16* kb = p.k + (long long)b * p.k_bs + (long long)h * D + lane * EPL;
@@ -492,6 +494,25 @@ extern "C" int vsb_attn_set_impl(int impl) {
   return VSB_OK;
 }
 
+extern "C" int vsb_attn_decode_bf16(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_rs,
+                                    long long k_bs, long long k_rs, long long v_bs, long long v_rs, long long o_bs,
+                                    long long o_rs, int B, int H, int Sq, int Sk, int D, int causal, float scale,
+                                    const void* k_start, void* stream) {
+  VSB_CHECK_ARG(q && k && v && o, "vsb_attn_decode_bf16: null pointer");
+  VSB_CHECK_ARG(D == 64 || D == 128, "vsb_attn_decode_bf16: head_dim %d unsupported (64/128)", D);
+  VSB_CHECK_ARG(B > 0 && H > 0 && Sq > 0 && Sk > 0 && Sq <= DEC_MAXQ, "vsb_attn_decode_bf16: bad shape (Sq=%d, at most %d)", Sq, DEC_MAXQ);
+  VSB_CHECK_ARG(q_rs % 4 == 0 && k_rs % 4 == 0 && v_rs % 4 == 0 && q_bs % 4 == 0 && k_bs % 4 == 0 && v_bs % 4 == 0 &&
+                    ((uintptr_t)q & 7) == 0 && ((uintptr_t)k & 7) == 0 && ((uintptr_t)v & 7) == 0,
+                "vsb_attn_decode_bf16: q/k/v must be 8-byte aligned with strides that are multiples of 4 elements");
+  AttnParams pd;
+  pd.q = (const bf16*)q; pd.k = (const bf16*)k; pd.v = (const bf16*)v; pd.o = (bf16*)o;
+  pd.q_bs = q_bs; pd.q_rs = q_rs; pd.k_bs = k_bs; pd.k_rs = k_rs; pd.v_bs = v_bs; pd.v_rs = v_rs; pd.o_bs = o_bs; pd.o_rs = o_rs;
+  pd.B = B; pd.H = H; pd.Sq = Sq; pd.Sk = Sk; pd.causal = causal;
+  pd.scale_log2 = scale * 1.4426950408889634f;
+  pd.k_start = reinterpret_cast<const int*>(k_start);
+  return D == 64 ? launch_decode<64>(pd, reinterpret_cast<cudaStream_t>(stream)) : launch_decode<128>(pd, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int vsb_flash_attn_bf16(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_rs,
                                    long long k_bs, long long k_rs, long long v_bs, long long v_rs, long long o_bs,
                                    long long o_rs, int B, int H, int Sq, int Sk, int D, int causal, float scale, void* stream) {
@@ -503,15 +524,8 @@ extern "C" int vsb_flash_attn_bf16(const void* q, const void* k, const void* v, 
                 "vsb_flash_attn_bf16: strides must be multiples of 8 elements (16 B)");
   VSB_CHECK_ARG(((uintptr_t)q & 15) == 0 && ((uintptr_t)k & 15) == 0 && ((uintptr_t)v & 15) == 0 && ((uintptr_t)o & 15) == 0,
                 "vsb_flash_attn_bf16: pointers must be 16-byte aligned");
-  if (g_attn_impl == 4 || (g_attn_impl == 0 && Sq <= DEC_MAXQ && Sk >= 64)) {
-    VSB_CHECK_ARG(Sq <= DEC_MAXQ, "vsb_flash_attn_bf16: decode kernel forced but Sq=%d > %d", Sq, DEC_MAXQ);
-    AttnParams pd;
-    pd.q = (const bf16*)q; pd.k = (const bf16*)k; pd.v = (const bf16*)v; pd.o = (bf16*)o;
-    pd.q_bs = q_bs; pd.q_rs = q_rs; pd.k_bs = k_bs; pd.k_rs = k_rs; pd.v_bs = v_bs; pd.v_rs = v_rs; pd.o_bs = o_bs; pd.o_rs = o_rs;
-    pd.B = B; pd.H = H; pd.Sq = Sq; pd.Sk = Sk; pd.causal = causal;
-    pd.scale_log2 = scale * 1.4426950408889634f;
-    return D == 64 ? launch_decode<64>(pd, reinterpret_cast<cudaStream_t>(stream)) : launch_decode<128>(pd, reinterpret_cast<cudaStream_t>(stream));
-  }
+  if (g_attn_impl == 4 || (g_attn_impl == 0 && Sq <= DEC_MAXQ && Sk >= 64))
+    return vsb_attn_decode_bf16(q, k, v, o, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, B, H, Sq, Sk, D, causal, scale, nullptr, stream);
   if (g_attn_impl == 2 || (g_attn_impl == 0 && Sq >= 64))
     return vsb_flash_attn_tc(q, k, v, o, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, B, H, Sq, Sk, D, causal, scale,
                              reinterpret_cast<cudaStream_t>(stream));

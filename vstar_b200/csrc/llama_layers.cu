@@ -20,11 +20,12 @@
 
 extern "C" int vsb_llama_layers(const vsb_llama_layer_t* layers, int n_layers, void* x, int B, int Tn, int past, void* cache, int Bc,
                                 int Tmax, int d, int H, int inter, float rms_eps, const void* rope_cos, const void* rope_sin,
-                                void* scratch, void* stream) {
+                                const void* positions, const void* k_start, void* scratch, void* stream) {
   VSB_CHECK_ARG(layers && x && cache && rope_cos && rope_sin && scratch, "vsb_llama_layers: null pointer");
   VSB_CHECK_ARG(n_layers > 0 && B > 0 && Tn > 0 && past >= 0 && d > 0 && H > 0 && inter > 0, "vsb_llama_layers: bad shape");
   VSB_CHECK_ARG(B <= Bc && past + Tn <= Tmax, "vsb_llama_layers: B=%d Tn=%d past=%d exceed the cache [%d, %d]", B, Tn, past, Bc, Tmax);
   VSB_CHECK_ARG(d % H == 0, "vsb_llama_layers: hidden %d not divisible by heads %d", d, H);
+  VSB_CHECK_ARG(k_start == nullptr || Tn <= 4, "vsb_llama_layers: ragged batches (k_start) need Tn <= 4, got %d", Tn);
   const int hd = d / H;
   const long long rows = (long long)B * Tn;
   const long long ld = 3LL * d;
@@ -38,9 +39,13 @@ extern "C" int vsb_llama_layers(const vsb_llama_layer_t* layers, int n_layers, v
     bf16* cl = reinterpret_cast<bf16*>(cache) + (long long)li * Bc * Tmax * ld;       // [Bc*Tmax, 3d]
     VSB_TRY(vsb_rmsnorm_bf16(xb, d, L.ln1, h, d, (int)rows, d, rms_eps, stream));
     VSB_TRY(vsb_gemm_bf16(h, d, L.wqkv, d, cl, ld, (int)rows, 3 * d, d, nullptr, nullptr, 0, VSB_EPI_NONE, 0, Tn, Tmax, past, stream));
-    VSB_TRY(vsb_rope_bf16(cl, ld, (int)rows, Tn, H, hd, past, rope_cos, rope_sin, nullptr, Tmax, past, stream));
-    VSB_TRY(vsb_flash_attn_bf16(cl + (long long)past * ld, cl + d, cl + 2 * d, attn, (long long)Tmax * ld, ld, (long long)Tmax * ld, ld,
-                                (long long)Tmax * ld, ld, (long long)Tn * d, d, B, H, Tn, past + Tn, hd, 1, scale, stream));
+    VSB_TRY(vsb_rope_bf16(cl, ld, (int)rows, Tn, H, hd, past, rope_cos, rope_sin, positions, Tmax, past, stream));
+    if (k_start != nullptr)
+      VSB_TRY(vsb_attn_decode_bf16(cl + (long long)past * ld, cl + d, cl + 2 * d, attn, (long long)Tmax * ld, ld, (long long)Tmax * ld, ld,
+                                   (long long)Tmax * ld, ld, (long long)Tn * d, d, B, H, Tn, past + Tn, hd, 1, scale, k_start, stream));
+    else
+      VSB_TRY(vsb_flash_attn_bf16(cl + (long long)past * ld, cl + d, cl + 2 * d, attn, (long long)Tmax * ld, ld, (long long)Tmax * ld, ld,
+                                  (long long)Tmax * ld, ld, (long long)Tn * d, d, B, H, Tn, past + Tn, hd, 1, scale, stream));
     VSB_TRY(vsb_gemm_bf16(attn, d, L.wo, d, xb, d, (int)rows, d, d, nullptr, xb, d, VSB_EPI_NONE, 0, 0, 0, 0, stream));
     VSB_TRY(vsb_rmsnorm_bf16(xb, d, L.ln2, h, d, (int)rows, d, rms_eps, stream));
     VSB_TRY(vsb_gemm_bf16(h, d, L.wgu, d, gu, inter, (int)rows, 2 * inter, d, nullptr, nullptr, 0, VSB_EPI_SWIGLU, 0, 0, 0, 0, stream));

@@ -247,7 +247,7 @@ class LlamaClipCore:
             self._cache_shape = shape
         return self._cache
 
-    def _llm_layers(self, x, B, Tn, past, Tmax):
+    def _llm_layers(self, x, B, Tn, past, Tmax, positions=None, k_start=None, cache_row_offset=0):
         """Run all decoder layers over the Tn new rows per sequence in x [B*Tn, d] (in place on the residual stream).
         Fused q|k|v rows live in the per-layer cache [B, Tmax, 3d] at positions past..past+Tn.  One native call
         (csrc/llama_layers.cu) sequences the 8 kernels of every layer: RMSNorm, QKV GEMM writing cache rows, RoPE in
@@ -258,7 +258,8 @@ class LlamaClipCore:
         Bc, Tm = self._cache_shape[1], self._cache_shape[2]
         scratch = torch.empty((B * Tn * (2 * c.hidden + c.intermediate),), dtype=BF, device=self.dev)
         return ops.llama_layers(self._layer_table, len(self.w.layers), x, B, Tn, past, self._cache, Bc, Tm, c.hidden, c.n_heads,
-                                c.intermediate, c.rms_eps, self.w.rope_cos, self.w.rope_sin, scratch)
+                                c.intermediate, c.rms_eps, self.w.rope_cos, self.w.rope_sin, scratch, positions=positions,
+                                k_start=k_start, cache_row_offset=cache_row_offset)
 
     def _logits_rows(self, x, rows):
         """final RMSNorm + lm_head on selected rows of the residual stream -> (hidden [n,d], argmax [n], logits fp32 [n,V])"""

@@ -201,6 +201,59 @@ class VQAEngine(LlamaClipCore):
             past += 1
         return out
 
+    # ------------------------------------------------------------------ continuous-batched greedy decode
+    def prefill_ragged(self, xs):
+        """xs: list of [T_b, d] input embeddings (consumed).  Sequences are LEFT-padded in the shared cache: sequence b
+        occupies cache rows [Tpad - T_b, Tpad) of batch slot b, so every sequence ends at the same row and one decode
+        step is ONE set of kernels for the whole batch (each weight byte read once for B tokens).
+        -> (last-position logits fp32 [B, V], Tpad, lengths)"""
+        B = len(xs)
+        lens = [int(x.shape[0]) for x in xs]
+        Tpad = max(lens)
+        assert Tpad < self.max_tokens
+        self._ensure_cache(B, self.max_tokens)
+        Tm = self._cache_shape[2]
+        last = []
+        for b, x in enumerate(xs):
+            self._llm_layers(x, 1, lens[b], 0, Tm, cache_row_offset=b * Tm + (Tpad - lens[b]))
+            last.append(x[-1:])
+        hn = ops.rmsnorm(torch.cat(last, 0).contiguous(), self.w.final_norm, self.cfg.rms_eps)
+        return ops.gemm(hn, self.w.lm_head, out_dtype=torch.float32), Tpad, lens
+
+    def decode_ragged(self, tokens, lens, Tpad, step):
+        """one decode step for the left-padded batch: tokens int64 [B] (token `step` of every answer) -> logits fp32 [B, V]"""
+        B = len(lens)
+        ids = torch.as_tensor(tokens, dtype=torch.int64, device=self.dev)
+        x = ops.gather_rows(ids, self.w.embed)
+        positions = torch.tensor([n + step for n in lens], dtype=torch.int32, device=self.dev)
+        k_start = torch.tensor([Tpad - n for n in lens], dtype=torch.int32, device=self.dev)
+        self._llm_layers(x, B, 1, Tpad + step, self._cache_shape[2], positions=positions, k_start=k_start)
+        hn = ops.rmsnorm(x, self.w.final_norm, self.cfg.rms_eps)
+        return ops.gemm(hn, self.w.lm_head, out_dtype=torch.float32)
+
+    def generate_batch(self, requests, max_new_tokens=200, eos_token_id=2, stop_ids=None):
+        """greedy generation for several (input_ids, image, object_crops, images_long, objects_long) requests at once.
+        Same per-sequence semantics as generate(); finished sequences idle (their slots keep stepping, results ignored).
+        -> list of new-token lists"""
+        xs = [self.build_embeds(ids, img, crops, il, ol) for ids, img, crops, il, ol in requests]
+        logits, Tpad, lens = self.prefill_ragged(xs)
+        B = len(xs)
+        outs = [[] for _ in range(B)]
+        done = [False] * B
+        for step in range(max_new_tokens):
+            nxt = ops.argmax_rows(logits)[0].tolist()              # one D2H per step for the whole batch
+            for b in range(B):
+                if done[b]:
+                    continue
+                outs[b].append(int(nxt[b]))
+                if nxt[b] == eos_token_id or (stop_ids and outs[b][-len(stop_ids):] == list(stop_ids)) or \
+                        Tpad + step >= self.max_tokens - 1:
+                    done[b] = True
+            if all(done) or step == max_new_tokens - 1:
+                break
+            logits = self.decode_ragged(nxt, lens, Tpad, step)
+        return outs
+
     def option_losses(self, question_ids, options_ids, image, object_crops=None, images_long=None, objects_long=None):
         """multiple_choices_inference core (vstar_bench_eval.py:127-163): the question prefix is prefilled ONCE; every
         option is appended on top of the cached prefix (its rows overwrite the previous option's) and scored by the mean
@@ -313,6 +366,29 @@ class VQA_LLM:
         if text.endswith(stop_str):
             text = text[:-len(stop_str)]
         return text.strip()
+
+    @torch.inference_mode()
+    def free_form_inference_batch(self, images, questions, max_new_tokens=200):
+        """free_form_inference for several (image, question) pairs in ONE continuous-batched decode (not in the reference,
+        which answers one image at a time, vstar_bench_eval.py:196): same prompt, stop string and post-processing per
+        sample; each decode step reads the 7B weights once for the whole batch."""
+        stop_str = "</s>"
+        kw = self.tokenizer(stop_str).input_ids
+        if len(kw) > 1 and kw[0] == self.tokenizer.bos_token_id:
+            kw = kw[1:]
+        reqs = []
+        for image, question in zip(images, questions):
+            ids = tokenizer_image_object_token(build_prompt_v1(DEFAULT_IMAGE_TOKEN + "\n" + question), self.tokenizer)
+            img, _ = self._pixels(image, None)
+            reqs.append((ids, img, None, None, None))
+        outs = self.engine.generate_batch(reqs, max_new_tokens, self.eos, stop_ids=kw)
+        texts = []
+        for out in outs:
+            text = self.tokenizer.batch_decode([out], skip_special_tokens=True)[0].strip()
+            if text.endswith(stop_str):
+                text = text[:-len(stop_str)]
+            texts.append(text.strip())
+        return texts
 
     @torch.inference_mode()
     def multiple_choices_inference(self, image, question, options, object_crops=None, images_long=None, objects_long=None):
