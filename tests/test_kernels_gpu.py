@@ -31,7 +31,7 @@ def rel_err(a, b):
 GEMM_SHAPES = [
     (128, 128, 64), (128, 256, 128), (256, 512, 256), (1, 128, 64), (5, 4, 768), (257, 1024, 1024),
     (300, 514, 768), (640, 11008, 512), (2304, 768, 768), (320, 4096, 4096), (77, 200, 592), (128, 64, 2304),
-    (1280, 8192, 1024),
+    (1280, 8192, 1024), (16, 4096, 2048), (5, 4096, 1024), (100, 1056, 512),
 ]
 
 
@@ -46,7 +46,7 @@ def test_gemm_plain(ops, M, N, K):
     assert torch.allclose(out.float(), ref, rtol=1e-2, atol=2e-2), rel_err(out, ref)
 
 
-@pytest.mark.parametrize("bn", [64, 128, 256])
+@pytest.mark.parametrize("bn", [32, 64, 128, 256])
 def test_gemm_forced_tile(ops, bn):
     from vstar_b200 import _lib
     M, N, K = 384, 768, 320
@@ -185,11 +185,11 @@ def test_attn_decode_kernel_shapes(ops, D, causal, Sq, Sk):
 
 
 @pytest.mark.parametrize("M,N,K", [(1, 4096, 4096), (1, 1001, 1000), (2, 514, 768), (3, 77, 11008), (4, 2048, 264), (5, 333, 2048),
-                                   (8, 12288, 1024), (7, 32004, 512)])
+                                   (8, 12288, 1024), (7, 32004, 512), (9, 4096, 4096), (16, 1000, 1192), (13, 22016, 256)])
 def test_gemm_skinny(ops, M, N, K):
-    """decode-sized problems (M <= 2 in production, up to 8 when forced) take the CUDA-core weight-streaming kernel
-    (gemm_skinny.cu); it must agree with the
-    fp32 reference AND with the tcgen05 kernel on every epilogue variant (same semantics behind vsb_gemm_bf16)"""
+    """decode-sized problems take the weight-streaming kernels of gemm_skinny.cu (CUDA-core FMA kernel for M <= 2, mma.sync
+    kernel up to M = 16); both must agree with the fp32 reference AND with the tcgen05 kernel on every epilogue variant
+    (same semantics behind vsb_gemm_bf16)"""
     from vstar_b200 import _lib
     a, w, b = rnd(M, K, seed=61), rnd(N, K, scale=1 / math.sqrt(K), seed=62), rnd(N, seed=63)
     r, r32 = rnd(M, N, seed=64), torch.randn(M, N, device="cuda")
@@ -202,24 +202,24 @@ def test_gemm_skinny(ops, M, N, K):
             o.append(ops.gemm(a, w, epilogue=ops.EPI_SWIGLU))
         return o
 
-    _lib.call("vsb_gemm_set_tuning", 1, 0)            # force the skinny kernel (errors out if it cannot take the shape)
+    got = {}
     try:
-        sk = run_all()
-        _lib.call("vsb_gemm_set_tuning", 64, 0)       # tcgen05 single-CTA kernel
-        tc = run_all()
+        for variant in ([1] if M <= 8 else []) + [2, 64]:   # 1 = FMA kernel, 2 = mma.sync kernel, 64 = tcgen05 single-CTA kernel
+            _lib.call("vsb_gemm_set_tuning", variant, 0)     # forcing a skinny variant errors out if it cannot take the shape
+            got[variant] = run_all()
     finally:
         _lib.call("vsb_gemm_set_tuning", 0, 0)
     auto = ops.gemm(a, w, out_dtype=torch.float32)
-    assert torch.equal(auto, sk[0] if M <= 2 else tc[0]) or M > 2      # production dispatch = skinny kernel for M <= 2
+    assert torch.equal(auto, got[1 if M == 1 else (2 if (M <= 8 or N <= 8192) else 64)][0])      # production dispatch
     y = a.float() @ w.float().t()
     yb = y + b.float()
     refs = [y, yb * torch.sigmoid(1.702 * yb) + r.float(), F.gelu(yb), F.relu(y) + r.float(), yb + r32]
     if N % 2 == 0:
         refs.append(F.silu(y[:, 0::2]) * y[:, 1::2])
-    for i, (s_, t_, ref) in enumerate(zip(sk, tc, refs)):
-        tol = dict(rtol=1e-4, atol=1e-3) if s_.dtype == torch.float32 else dict(rtol=1e-2, atol=3e-2)
-        assert s_.shape == ref.shape and torch.allclose(s_.float(), ref, **tol), (i, rel_err(s_, ref))
-        assert torch.allclose(s_.float(), t_.float(), **tol), (i, rel_err(s_, t_))
+    for variant, outs in got.items():
+        for i, (o_, ref) in enumerate(zip(outs, refs)):
+            tol = dict(rtol=1e-4, atol=1e-3) if o_.dtype == torch.float32 else dict(rtol=1e-2, atol=3e-2)
+            assert o_.shape == ref.shape and torch.allclose(o_.float(), ref, **tol), (variant, i, rel_err(o_, ref))
 
 
 def test_gemm_skinny_row_remap_strided(ops):
@@ -227,12 +227,19 @@ def test_gemm_skinny_row_remap_strided(ops):
     B, K, N, T, p0 = 3, 512, 384, 40, 17
     a_wide, w, b = rnd(B, 2 * K, seed=65), rnd(N, K, scale=1 / math.sqrt(K), seed=66), rnd(N, seed=67)
     buf = torch.zeros(B * T, 2 * N, dtype=BF, device="cuda")
-    ops.gemm(a_wide[:, K:], w, out=buf[:, N:], bias=b, rows_per_group=1, group_stride=T, group_offset=p0)
+    from vstar_b200 import _lib
     ref = a_wide[:, K:].float() @ w.float().t() + b.float()
-    got = buf.view(B, T, 2 * N)
-    assert torch.allclose(got[:, p0, N:].float(), ref, rtol=1e-2, atol=2e-2)
-    got[:, p0, N:] = 0
-    assert float(got.abs().max()) == 0
+    for variant in (1, 2):
+        buf.zero_()
+        _lib.call("vsb_gemm_set_tuning", variant, 0)
+        try:
+            ops.gemm(a_wide[:, K:], w, out=buf[:, N:], bias=b, rows_per_group=1, group_stride=T, group_offset=p0)
+        finally:
+            _lib.call("vsb_gemm_set_tuning", 0, 0)
+        got = buf.view(B, T, 2 * N)
+        assert torch.allclose(got[:, p0, N:].float(), ref, rtol=1e-2, atol=2e-2)
+        got[:, p0, N:] = 0
+        assert float(got.abs().max()) == 0
 
 
 def test_layernorm_rmsnorm(ops):

@@ -336,6 +336,7 @@ constexpr int DEC_U = 4;          // keys in flight per warp
 
 template <int D>
 __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_kernel(const AttnParams p) {
+  pdl_prologue();
   constexpr int EPL = D / 32;                                   // elements per lane
   cg::cluster_group cluster = cg::this_cluster();
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -470,19 +471,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_kernel(const AttnP
 
 template <int D>
 static int launch_decode(const AttnParams& p, cudaStream_t st) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(DEC_SPLITS, p.H, p.B);
-  cfg.blockDim = dim3(DEC_WARPS * 32);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = DEC_SPLITS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  VSB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_kernel<D>, p));
+  VSB_CUDA(vsb_launch_pdl(attn_decode_kernel<D>, dim3(DEC_SPLITS, p.H, p.B), dim3(DEC_WARPS * 32), 0, st, DEC_SPLITS, p));
   return VSB_OK;
 }
 

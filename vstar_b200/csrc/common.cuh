@@ -95,6 +95,42 @@ __device__ __forceinline__ float silu_f(float x) {
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
 
+// ---------------------------------------------------------------- programmatic dependent launch (decode chain)
+// A decode step is ~260 kernels of a few microseconds each on one stream; the gap between dependent kernels (drain, launch,
+// CTA scheduling) is as long as many of the kernels.  Kernels launched with vsb_launch_pdl may become resident while their
+// predecessor is still running; pdl_prologue() - the FIRST statement of such a kernel - lets the successor do the same and
+// then blocks until the predecessor grid has completed and its writes are visible (griddepcontrol.wait), so nothing is read
+// or written early.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t vsb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                                         Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[n].val.programmaticStreamSerializationAllowed = 1;
+  ++n;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static inline int vsb_num_sms() {
   static int n = 0;
   if (n == 0) {

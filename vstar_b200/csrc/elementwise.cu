@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(128) rmsnorm_kernel(const bf16* __restrict__ x
 // (above) serialises 16 dependent-latency loads and measured 11 us for one 4096-wide row.  Same arithmetic, same rounding.
 __global__ void __launch_bounds__(256) rmsnorm_row_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ w,
                                                           bf16* __restrict__ y, long long ldy, int cols, float eps) {
+  pdl_prologue();
   __shared__ float red[32];
   const bf16* xr = x + (long long)blockIdx.x * ldx;
   bf16* yr = y + (long long)blockIdx.x * ldy;
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(256) rmsnorm_row_kernel(const bf16* __restrict
 __global__ void rope_kernel(bf16* __restrict__ qkv, long long ld, int rows, int T, int H, int D, int pos0,
                             const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t, const int* __restrict__ positions,
                             long long group_stride, long long group_offset) {
+  pdl_prologue();
   const int row = blockIdx.x;
   if (row >= rows) return;
   const int pos = positions ? positions[row] : pos0 + (row % T);
@@ -405,8 +407,8 @@ extern "C" int vsb_rmsnorm_bf16(const void* x, long long ldx, const void* w, voi
   if (rows <= 0) return VSB_OK;
   const int blocks = (rows + 3) / 4;
   if (rows <= 32 && cols >= 2048 && cols <= 8192) {
-    rmsnorm_row_kernel<<<rows, 256, 0, STREAM(stream)>>>((const bf16*)x, ldx, (const bf16*)w, (bf16*)y, ldy, cols, eps);
-    VSB_LAUNCH_CHECK();
+    VSB_CUDA(vsb_launch_pdl(rmsnorm_row_kernel, dim3(rows), dim3(256), 0, STREAM(stream), 1, (const bf16*)x, ldx, (const bf16*)w, (bf16*)y,
+                            ldy, cols, eps));
     return VSB_OK;
   }
   if (cols <= 1024)
@@ -422,9 +424,8 @@ extern "C" int vsb_rope_bf16(void* qkv, long long ld, int rows, int T, int H, in
                              void* stream) {
   VSB_CHECK_ARG(qkv && cos_table && sin_table && rows >= 0 && T > 0 && H > 0 && D % 16 == 0 && ld % 8 == 0, "vsb_rope_bf16: bad args (D % 16, ld % 8)");
   if (rows == 0) return VSB_OK;
-  rope_kernel<<<rows, 256, 0, STREAM(stream)>>>((bf16*)qkv, ld, rows, T, H, D, pos0, (const bf16*)cos_table, (const bf16*)sin_table,
-                                                (const int*)positions, group_stride, group_offset);
-  VSB_LAUNCH_CHECK();
+  VSB_CUDA(vsb_launch_pdl(rope_kernel, dim3(rows), dim3(256), 0, STREAM(stream), 1, (bf16*)qkv, ld, rows, T, H, D, pos0,
+                          (const bf16*)cos_table, (const bf16*)sin_table, (const int*)positions, group_stride, group_offset));
   return VSB_OK;
 }
 

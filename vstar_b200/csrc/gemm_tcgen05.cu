@@ -147,7 +147,7 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : (BN == 64 ? 8 : 10));
   static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;           // 8 epilogue warps x EPI_WARP_BYTES staging
   static constexpr int BAR_OFFSET = EPI_OFFSET + 8 * 2560;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
@@ -892,8 +892,8 @@ extern "C" int vsb_gemm_set_group_m(int group_m) {
   return VSB_OK;
 }
 
-int vsb_gemm_skinny_launch(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
-                           const void* bias, const void* residual, long long ldr, int epilogue, int out_fp32, int rows_per_group,
+int vsb_gemm_skinny_launch(int variant, const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N,
+                           int K, const void* bias, const void* residual, long long ldr, int epilogue, int out_fp32, int rows_per_group,
                            long long group_stride, long long group_offset, cudaStream_t stream);
 
 // ---------------------------------------------------------------- CUDA-event profiling of every launch (bench.py roofline leg)
@@ -986,12 +986,19 @@ static int gemm_dispatch(const void* A, long long lda, const void* W, long long 
   p.group_offset = group_offset;
 
   // decode-sized problems are HBM-bound on W: CUDA-core streaming kernel (gemm_skinny.cu); force_bn = 1 forces it (tests)
-  // measured (tools/bench_vqa.py, CUDA-graph timing): 0.57-0.95 of the HBM roofline at M = 1, ahead of the tcgen05 tiles up to
-  // M = 2; from M = 3 the CUDA-core FMAs/unpacks bind and the tensor-core kernel (0.63-0.76 at M = 16) wins
-  if (((g_force_bn == 0 && M <= 2) || (g_force_bn == 1 && M <= 8)) && (K % 8) == 0)
-    return vsb_gemm_skinny_launch(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, epilogue, out_fp32, rows_per_group, group_stride,
-                                  group_offset, stream);
-  VSB_CHECK_ARG(g_force_bn != 1, "vsb_gemm_bf16: skinny kernel forced but M=%d > 8 or K %% 8 != 0", M);
+  // measured (tools/bench_vqa.py, CUDA-graph timing, fraction of the HBM roofline): FMA kernel 0.57-0.96 at M = 1; mma.sync
+  // kernel 0.44-0.79 for M = 2..8 (and ahead of the tcgen05 tiles on N <= 8192 up to M = 16); tcgen05 tiles 0.26-0.76 at M = 16
+  if ((K % 8) == 0) {
+    int variant = 0;
+    if (g_force_bn == 1 && M <= 8) variant = 1;
+    else if (g_force_bn == 2 && M <= 16) variant = 2;
+    else if (g_force_bn == 0 && M == 1) variant = 1;
+    else if (g_force_bn == 0 && (M <= 8 || (M <= 16 && N <= 8192))) variant = 2;   // measured per shape, tools/bench_vqa.py
+    if (variant)
+      return vsb_gemm_skinny_launch(variant, A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, epilogue, out_fp32, rows_per_group,
+                                    group_stride, group_offset, stream);
+  }
+  VSB_CHECK_ARG(g_force_bn != 1 && g_force_bn != 2, "vsb_gemm_bf16: skinny kernel forced but M=%d too large or K %% 8 != 0", M);
   const int sms = g_max_ctas > 0 ? g_max_ctas : vsb_num_sms();
   // tile-width choice: minimise (waves * BN) ~ time; prefer the wider tile on ties (less A re-streaming)
   int bn = 64;
@@ -1010,6 +1017,9 @@ static int gemm_dispatch(const void* A, long long lda, const void* W, long long 
       if (best < 0 || cost < best) { best = cost; bn = c; }
     }
   }
+  // batched decode (M <= 128) on the N = 4096 projections: 64-wide tiles give only 64 CTAs, each streaming a long K; 32-wide
+  // tiles put twice as many SMs on the weight stream (the problem is HBM-bound on W)
+  if (g_force_bn == 0 && bn == 64 && (long long)((M + BM - 1) / BM) * ((N + 63) / 64) <= sms / 2 && N >= 64) bn = 32;
   p.group_m = g_group_m > 0 ? g_group_m : 16;      // 2048-row bands (single-CTA tiles)
   CUtensorMap tmA, tmB;
   int r = make_tensor_map(&tmA, A, M, K, lda, BM);
@@ -1033,5 +1043,6 @@ static int gemm_dispatch(const void* A, long long lda, const void* W, long long 
   if (r) return r;
   if (bn == 256) return launch_gemm<256>(tmA, tmB, p, sms, stream);
   if (bn == 128) return launch_gemm<128>(tmA, tmB, p, sms, stream);
+  if (bn == 32) return launch_gemm<32>(tmA, tmB, p, sms, stream);
   return launch_gemm<64>(tmA, tmB, p, sms, stream);
 }
