@@ -329,35 +329,36 @@ int vsb_flash_attn_tc(const void* q, const void* k, const void* v, void* o, long
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
-constexpr int DEC_SPLITS = 8;     // cluster size
-constexpr int DEC_WARPS = 4;
+constexpr int DEC_SPLITS = 8;     // largest cluster size
+constexpr int DEC_WARPS = 8;
 constexpr int DEC_MAXQ = 4;
-constexpr int DEC_U = 4;          // keys in flight per warp
+constexpr int DEC_U = 8;          // keys in flight per warp
 
-template <int D>
-__global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_kernel(const AttnParams p) {
+template <int D, int NQ>      // NQ = compile-time bound on Sq (1 for plain decode, NQ otherwise)
+__global__ void __launch_bounds__(DEC_WARPS * 32, 2) attn_decode_kernel(const AttnParams p) {
   pdl_prologue();
   constexpr int EPL = D / 32;                                   // elements per lane
   cg::cluster_group cluster = cg::this_cluster();
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __shared__ float s_m[DEC_WARPS][DEC_MAXQ], s_l[DEC_WARPS][DEC_MAXQ];
-  __shared__ float s_acc[DEC_WARPS][DEC_MAXQ][D];
-  __shared__ float c_m[DEC_MAXQ], c_l[DEC_MAXQ];                // this CTA's combined partial (read remotely by rank 0)
-  __shared__ float c_acc[DEC_MAXQ][D];
+  __shared__ float s_m[DEC_WARPS][NQ], s_l[DEC_WARPS][NQ];
+  __shared__ float s_acc[DEC_WARPS][NQ][D];
+  __shared__ float c_m[NQ], c_l[NQ];                // this CTA's combined partial (read remotely by rank 0)
+  __shared__ float c_acc[NQ][D];
 
   const int off = p.Sk - p.Sq;
   const int k_first = p.k_start ? max(0, min(p.k_start[b], p.Sk)) : 0;
-  const int chunk = (p.Sk - k_first + DEC_SPLITS - 1) / DEC_SPLITS;
+  const int nsplit = gridDim.x;                                 // = cluster size (1, 2, 4 or 8)
+  const int chunk = (p.Sk - k_first + nsplit - 1) / nsplit;
   const int k_begin = k_first + split * chunk;
   const int k_end = min(p.Sk, k_begin + chunk);
   const bf16* qb = p.q + (long long)b * p.q_bs + (long long)h * D + lane * EPL;
   const bf16* kb = p.k + (long long)b * p.k_bs + (long long)h * D + lane * EPL;
   const bf16* vb = p.v + (long long)b * p.v_bs + (long long)h * D + lane * EPL;
 
-  float q[DEC_MAXQ][EPL], acc[DEC_MAXQ][EPL], m[DEC_MAXQ], l[DEC_MAXQ];
+  float q[NQ][EPL], acc[NQ][EPL], m[NQ], l[NQ];
 #pragma unroll
-  for (int qi = 0; qi < DEC_MAXQ; ++qi) {
+  for (int qi = 0; qi < NQ; ++qi) {
     m[qi] = -INFINITY;
     l[qi] = 0.f;
 #pragma unroll
@@ -368,33 +369,28 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_kernel(const AttnP
   }
 
   for (int j0 = k_begin + warp; j0 < k_end; j0 += DEC_WARPS * DEC_U) {
-    float kf[DEC_U][EPL], vf[DEC_U][EPL];
+    // K / V rows stay packed (bf16 pairs) until they are used: 2 x EPL/2 registers per key in flight
+    uint32_t kr[DEC_U][EPL / 2], vr[DEC_U][EPL / 2];
 #pragma unroll
     for (int u = 0; u < DEC_U; ++u) {
       const int j = j0 + u * DEC_WARPS;
       if (j < k_end) {
         if (EPL == 4) {
-          const uint2 kr = *reinterpret_cast<const uint2*>(kb + (long long)j * p.k_rs);
-          const uint2 vr = *reinterpret_cast<const uint2*>(vb + (long long)j * p.v_rs);
-          float2 t;
-          t = unpack_bf16x2(kr.x); kf[u][0] = t.x; kf[u][1] = t.y;
-          t = unpack_bf16x2(kr.y); kf[u][2 % EPL] = t.x; kf[u][3 % EPL] = t.y;
-          t = unpack_bf16x2(vr.x); vf[u][0] = t.x; vf[u][1] = t.y;
-          t = unpack_bf16x2(vr.y); vf[u][2 % EPL] = t.x; vf[u][3 % EPL] = t.y;
+          const uint2 k2 = *reinterpret_cast<const uint2*>(kb + (long long)j * p.k_rs);
+          const uint2 v2 = *reinterpret_cast<const uint2*>(vb + (long long)j * p.v_rs);
+          kr[u][0] = k2.x; kr[u][(EPL / 2) - 1] = k2.y;
+          vr[u][0] = v2.x; vr[u][(EPL / 2) - 1] = v2.y;
         } else {
-          const uint32_t kr = *reinterpret_cast<const uint32_t*>(kb + (long long)j * p.k_rs);
-          const uint32_t vr = *reinterpret_cast<const uint32_t*>(vb + (long long)j * p.v_rs);
-          float2 t;
-          t = unpack_bf16x2(kr); kf[u][0] = t.x; kf[u][1] = t.y;
-          t = unpack_bf16x2(vr); vf[u][0] = t.x; vf[u][1] = t.y;
+          kr[u][0] = *reinterpret_cast<const uint32_t*>(kb + (long long)j * p.k_rs);
+          vr[u][0] = *reinterpret_cast<const uint32_t*>(vb + (long long)j * p.v_rs);
         }
       } else {
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) kf[u][e] = vf[u][e] = 0.f;
+        for (int e = 0; e < EPL / 2; ++e) kr[u][e] = vr[u][e] = 0u;
       }
     }
 #pragma unroll
-    for (int qi = 0; qi < DEC_MAXQ; ++qi) {
+    for (int qi = 0; qi < NQ; ++qi) {
       if (qi < p.Sq) {                                          // warp-uniform
         const int jmax = p.causal ? qi + off : p.Sk - 1;
         float sc[DEC_U];
@@ -403,7 +399,11 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_kernel(const AttnP
         for (int u = 0; u < DEC_U; ++u) {
           float d = 0.f;
 #pragma unroll
-          for (int e = 0; e < EPL; ++e) d = fmaf(q[qi][e], kf[u][e], d);
+          for (int e = 0; e < EPL / 2; ++e) {
+            const float2 kk = unpack_bf16x2(kr[u][e]);
+            d = fmaf(q[qi][2 * e], kk.x, d);
+            d = fmaf(q[qi][2 * e + 1], kk.y, d);
+          }
           d = warp_sum(d);
           const int j = j0 + u * DEC_WARPS;
           sc[u] = (j < k_end && j <= jmax) ? d : -INFINITY;
@@ -420,7 +420,11 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_kernel(const AttnP
             const float pr = exp2f(sc[u] - mx);
             ls += pr;
 #pragma unroll
-            for (int e = 0; e < EPL; ++e) acc[qi][e] = fmaf(pr, vf[u][e], acc[qi][e]);
+            for (int e = 0; e < EPL / 2; ++e) {
+              const float2 vv = unpack_bf16x2(vr[u][e]);
+              acc[qi][2 * e] = fmaf(pr, vv.x, acc[qi][2 * e]);
+              acc[qi][2 * e + 1] = fmaf(pr, vv.y, acc[qi][2 * e + 1]);
+            }
           }
           l[qi] = l[qi] * corr + ls;
         }
@@ -429,13 +433,13 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_kernel(const AttnP
   }
   // warps -> CTA partial
 #pragma unroll
-  for (int qi = 0; qi < DEC_MAXQ; ++qi) {
+  for (int qi = 0; qi < NQ; ++qi) {
     if (lane == 0) { s_m[warp][qi] = m[qi]; s_l[warp][qi] = l[qi]; }
 #pragma unroll
     for (int e = 0; e < EPL; ++e) s_acc[warp][qi][lane * EPL + e] = acc[qi][e];
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < DEC_MAXQ * D; idx += DEC_WARPS * 32) {
+  for (int idx = threadIdx.x; idx < NQ * D; idx += DEC_WARPS * 32) {
     const int qi = idx / D, d = idx - qi * D;
     float M = -INFINITY;
 #pragma unroll
@@ -455,9 +459,9 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_kernel(const AttnP
     for (int idx = threadIdx.x; idx < p.Sq * D; idx += DEC_WARPS * 32) {
       const int qi = idx / D, d = idx - qi * D;
       float M = -INFINITY;
-      for (int r = 0; r < DEC_SPLITS; ++r) M = fmaxf(M, *cluster.map_shared_rank(&c_m[qi], r));
+      for (int r = 0; r < nsplit; ++r) M = fmaxf(M, *cluster.map_shared_rank(&c_m[qi], r));
       float a = 0.f, ll = 0.f;
-      for (int r = 0; r < DEC_SPLITS; ++r) {
+      for (int r = 0; r < nsplit; ++r) {
         const float mr = *cluster.map_shared_rank(&c_m[qi], r);
         const float f = (mr == -INFINITY) ? 0.f : exp2f(mr - M);
         a += *cluster.map_shared_rank(&c_acc[qi][d], r) * f;
@@ -471,7 +475,14 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_kernel(const AttnP
 
 template <int D>
 static int launch_decode(const AttnParams& p, cudaStream_t st) {
-  VSB_CUDA(vsb_launch_pdl(attn_decode_kernel<D>, dim3(DEC_SPLITS, p.H, p.B), dim3(DEC_WARPS * 32), 0, st, DEC_SPLITS, p));
+  // keys of one (batch, head) are split over a cluster of 1..8 CTAs: as many as keep the machine filled about twice, but
+  // not so many that a CTA gets fewer than ~64 keys (a batched decode step already has B*H independent heads)
+  int splits = DEC_SPLITS;
+  while (splits > 1 && ((long long)splits * p.H * p.B > 2LL * vsb_num_sms() + p.H || p.Sk / splits < 64)) splits >>= 1;
+  if (p.Sq == 1)
+    VSB_CUDA(vsb_launch_pdl(attn_decode_kernel<D, 1>, dim3(splits, p.H, p.B), dim3(DEC_WARPS * 32), 0, st, splits, p));
+  else
+    VSB_CUDA(vsb_launch_pdl(attn_decode_kernel<D, DEC_MAXQ>, dim3(splits, p.H, p.B), dim3(DEC_WARPS * 32), 0, st, splits, p));
   return VSB_OK;
 }
 
