@@ -56,7 +56,7 @@ def test_fullwidth_two_layer_model():
     T = ids.shape[1] - 1 + 256
     x, T2, img_pos = eng.prefill(ids.cuda(), images_clip.to(BF).cuda())
     assert T2 == T
-    rows = torch.arange(T - 6, T, device="cuda")
+    rows = torch.tensor([eng.x_row(0, t) for t in range(T - 6, T)], device="cuda")
     hn, am, logits = eng._logits_rows(x, rows)
     ref_logits = o32["logits"][0, T - 6:T]
     assert logits.shape == ref_logits.shape

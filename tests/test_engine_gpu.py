@@ -133,6 +133,39 @@ def test_batched_equals_single(setup):
         assert int(logits[i].argmax()) == int(o1["pred_logits"][0].argmax())
 
 
+def test_shared_prefix_kv_equals_full_prefill(setup):
+    """the K/V rows of the constant text prefix (before <im_start>) are snapshotted by the first prefill and reused by later
+    ones, which then run the decoder only from <im_start> on: outputs must equal the full recomputation"""
+    O, cfg, sd, sd_bf, eng = setup
+    prompt, ans = O.synthetic_prompt(cfg, n_text=40, seed=8)
+    ids = torch.cat([prompt, ans.unsqueeze(0)], 1)
+    imgs = [synth_image(200 + i, 120 + 20 * i, 100 + 9 * i) for i in range(4)]
+    ic = torch.cat([O.preprocess_clip(i) for i in imgs]).to(BF).cuda()
+    io = torch.cat([O.preprocess_owl(i) for i in imgs]).to(BF).cuda()
+    idb = ids.expand(4, -1).contiguous().cuda()
+    keys = ("hidden_loc", "low_res_masks", "pred_logits", "pred_boxes")
+    eng.prefix_cache = False
+    try:
+        full = {k: v.clone() for k, v in eng.model_forward(io, ic, idb).items() if k in keys}
+        assert eng._P == 0
+    finally:
+        eng.prefix_cache = True
+    eng._prefix_ids = None                                 # forget whatever an earlier test left behind
+    first = {k: v.clone() for k, v in eng.model_forward(io[:2], ic[:2], idb[:2]).items() if k in keys}     # computes + snapshots
+    assert eng._P == 0 and eng._prefix_ids is not None
+    n0 = eng.stats["prefix_shared"]
+    shared = {k: v.clone() for k, v in eng.model_forward(io, ic, idb).items() if k in keys}                # 4 crops, 2 new slots
+    img_pos = int((ids[0] == -200).nonzero()[0, 0])
+    assert eng._P == img_pos - 1 and eng.stats["prefix_shared"] == n0 + 4
+    for k in keys:
+        assert err(first[k], full[k][:2]) < 1e-6, k
+        assert err(shared[k], full[k]) < 2e-3, (k, err(shared[k], full[k]))
+    REPORT["shared_prefix_err"] = {k: err(shared[k], full[k]) for k in keys}
+    # draft-verify path on top of the shared prefix
+    out = eng.inference(io, ic, prompt.expand(4, -1).contiguous(), ans.tolist(), forced_ids=ans.tolist())
+    assert err(out["low_res_masks"], full["low_res_masks"]) < 2e-3 and eng._P == img_pos - 1
+
+
 def test_zz_write_report(setup):
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(REPORT, open("gpurun_out/engine_parity_report.json", "w"), indent=1)

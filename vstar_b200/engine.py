@@ -199,7 +199,14 @@ class LlamaClipCore:
         self._cache = None
         self._cache_shape = None
         self._layer_table = None        # ctypes array of per-layer weight pointers for the native layer runner
-        self.stats = dict(verified=0, fallback=0)
+        self.stats = dict(verified=0, fallback=0, prefix_shared=0)
+        # shared-prefix KV (see prefill): the text before <im_start> is the same for every crop
+        self.prefix_cache = True
+        self._prefix_ids = None          # tuple of token ids
+        self._prefix_kv = None           # [n_layers, P, 3d] snapshot of the cache rows of that prefix
+        self._prefix_slots = 0           # cache slots whose rows 0..P currently hold it
+        self._P = 0                      # prefix rows omitted from the residual stream returned by the last prefill
+        self._Tn = 0
 
     # ------------------------------------------------------------------ ViT
     def _vit_forward(self, vw, pixels, patch, heads, image, eps):
@@ -245,6 +252,7 @@ class LlamaClipCore:
             self._cache = None
             self._cache = torch.empty(shape, dtype=BF, device=self.dev)
             self._cache_shape = shape
+            self._prefix_slots = 0
         return self._cache
 
     def _llm_layers(self, x, B, Tn, past, Tmax, positions=None, k_start=None, cache_row_offset=0):
@@ -270,9 +278,22 @@ class LlamaClipCore:
         idx, _ = ops.argmax_rows(logits)
         return hn, idx, logits
 
+    def x_row(self, b, pos):
+        """row of the residual stream returned by the last prefill() that holds spliced position `pos` of crop `b`"""
+        assert pos >= self._P, "position inside the shared prefix: its rows are not recomputed"
+        return b * self._Tn + pos - self._P
+
     def prefill(self, input_ids, images_clip):
         """input_ids int64 [B, L] (same L and same image position for the whole batch), images_clip [B,3,224,224] bf16.
-        Returns the residual stream x [B*T, d] (pre final norm), T."""
+        Returns (x, T, img_pos): the residual stream (pre final norm) of the rows that were computed, the spliced length T
+        and the image position.  Use x_row(b, pos) to address x.
+
+        Shared prefix: the tokens before <im_start> (the conversation's system prompt and "USER:",
+        conversation.py:355-365) are identical for every crop and, the model being causal, so are their K/V rows.  The
+        first prefill with a given prefix computes everything and snapshots those cache rows; later calls copy them into
+        the batch slots that lack them and run the decoder only over the T - P rows from <im_start> on (past = P).
+        Every remaining row sees bit-identical inputs, so the result is the unshared one, ~11 % fewer 7B FLOPs per crop.
+        `self.prefix_cache = False` switches it off."""
         c = self.cfg
         B, L = input_ids.shape
         pos = (input_ids[0] == IMAGE_TOKEN_INDEX).nonzero()
@@ -282,16 +303,40 @@ class LlamaClipCore:
         n_img = c.clip_tokens
         T = L - 1 + n_img
         assert T <= self.max_tokens
-        ct, S = self.clip_tokens(images_clip)                       # [B*257, Cc]
-        x = torch.empty((B * T, c.hidden), dtype=BF, device=self.dev)
-        # mm_projector over all B*257 rows in ONE GEMM whose epilogue scatters each crop's rows straight into the LLM
-        # input buffer: patch row i of crop b -> x[b*T + img_pos + i].  The CLS row lands on row img_pos-1 (the
-        # <im_start> slot, img_pos >= 1 because of BOS) and is overwritten by the embedding splice below.
         assert img_pos >= 1
-        ops.gemm(ct, self.w.mm_w, out=x, bias=self.w.mm_b, rows_per_group=S, group_stride=T, group_offset=img_pos - 1)
-        ops.embed_splice(input_ids.contiguous(), self.w.embed, x, img_pos, n_img)
         self._ensure_cache(B, self.max_tokens)
-        self._llm_layers(x, B, T, 0, self.max_tokens)
+        # P = rows before the <im_start> slot (the CLS row of the projector GEMM lands on that slot, see below)
+        P = 0
+        if self.prefix_cache and img_pos >= 2:
+            head = input_ids[:, :img_pos - 1]
+            if bool((head == head[0]).all()):
+                pid = tuple(head[0].tolist())
+                if pid == self._prefix_ids:
+                    P = len(pid)
+                else:                                   # new prefix: this call computes it in full and snapshots it below
+                    self._prefix_ids, self._prefix_kv, self._prefix_slots = None, None, 0
+        Tn = T - P
+        ct, S = self.clip_tokens(images_clip)                       # [B*257, Cc]
+        x = torch.empty((B * Tn, c.hidden), dtype=BF, device=self.dev)
+        # mm_projector over all B*257 rows in ONE GEMM whose epilogue scatters each crop's rows straight into the LLM
+        # input buffer: patch row i of crop b -> x[b*Tn + img_pos - P + i].  The CLS row lands on the <im_start> slot
+        # (img_pos - 1 >= P) and is overwritten by the embedding splice below.
+        ops.gemm(ct, self.w.mm_w, out=x, bias=self.w.mm_b, rows_per_group=S, group_stride=Tn, group_offset=img_pos - 1 - P)
+        ids_new = input_ids[:, P:].contiguous() if P else input_ids.contiguous()
+        ops.embed_splice(ids_new, self.w.embed, x, img_pos - P, n_img)
+        if P:
+            if self._prefix_slots < B:                  # slots that do not hold the prefix rows yet
+                self._cache[:, self._prefix_slots:B, :P].copy_(self._prefix_kv[:, None])
+                self._prefix_slots = B
+            self.stats["prefix_shared"] += B
+        self._llm_layers(x, B, Tn, P, self.max_tokens)
+        if not P and self.prefix_cache and img_pos >= 2 and self._prefix_ids is None:
+            head = input_ids[:, :img_pos - 1]
+            if bool((head == head[0]).all()):
+                self._prefix_ids = tuple(head[0].tolist())
+                self._prefix_kv = self._cache[:, 0, :img_pos - 1].clone()
+                self._prefix_slots = B                  # every slot of this batch just computed the same rows
+        self._P, self._Tn = P, Tn
         return x, T, img_pos
 
     def decode_step(self, tokens, B, past):
@@ -409,7 +454,7 @@ class VSMEngine(LlamaClipCore):
         for b in range(B):
             for k in (ids_cpu[b] == c.loc_token_idx).nonzero().flatten().tolist():
                 assert k - 1 > img_pos, "[LOC] before the image is outside the reference's 255-offset hack (VSM.py:230-234)"
-                rows.append(b * T + (k - 1) + c.clip_tokens - 1)
+                rows.append(self.x_row(b, (k - 1) + c.clip_tokens - 1))
                 crop_of_loc.append(b)
         if not rows:
             raise RuntimeError("no [LOC] token in input_ids: the reference fails here too (VSM.py:322 empty loop, visual_search.py:209-211)")
@@ -445,7 +490,7 @@ class VSMEngine(LlamaClipCore):
         x, T, img_pos = self.prefill(ids, images_clip)
         n_img = c.clip_tokens
         # rows that predict answer token j (j = 0..g-1): original index Lp-1+j -> spliced row +255
-        pred_rows = torch.tensor([b * T + (Lp - 1 + j) + n_img - 1 for b in range(B) for j in range(g)], dtype=torch.int64, device=self.dev)
+        pred_rows = torch.tensor([self.x_row(b, (Lp - 1 + j) + n_img - 1) for b in range(B) for j in range(g)], dtype=torch.int64, device=self.dev)
         hn, am, logits = self._logits_rows(x, pred_rows)
         am = am.view(B, g).cpu()
         ok = [bool((am[b] == draft.cpu()).all()) for b in range(B)] if forced_ids is None else [True] * B
@@ -463,7 +508,7 @@ class VSMEngine(LlamaClipCore):
         for b in range(B):
             for j, tok in enumerate(d_cpu):
                 if tok == c.loc_token_idx:
-                    rows.append(b * T + (Lp - 1 + j) + n_img - 1)
+                    rows.append(self.x_row(b, (Lp - 1 + j) + n_img - 1))
                     crop_of_loc.append(b)
         if not rows:
             raise RuntimeError("no [LOC] token generated (reference: IndexError at visual_search.py:209-211)")
@@ -477,7 +522,7 @@ class VSMEngine(LlamaClipCore):
         c = self.cfg
         assert prompt_ids.shape[0] == 1
         x, T, img_pos = self.prefill(prompt_ids.to(self.dev), images_clip)
-        last = torch.tensor([T - 1], dtype=torch.int64, device=self.dev)
+        last = torch.tensor([self.x_row(0, T - 1)], dtype=torch.int64, device=self.dev)
         hn, am, logits = self._logits_rows(x, last)
         out = prompt_ids[0].cpu().tolist()
         argmaxes = []
