@@ -296,6 +296,8 @@ class LlamaClipCore:
         `self.prefix_cache = False` switches it off."""
         c = self.cfg
         B, L = input_ids.shape
+        # all id bookkeeping on the host copy: nothing below may wait for the GPU (callers pipeline chunks, VSM._run)
+        input_ids = input_ids if input_ids.device.type == "cpu" else input_ids.cpu()
         pos = (input_ids[0] == IMAGE_TOKEN_INDEX).nonzero()
         assert pos.numel() == 1, "exactly one <image> placeholder expected (llava_arch.py:185-208)"
         img_pos = int(pos[0, 0])
@@ -322,7 +324,7 @@ class LlamaClipCore:
         # input buffer: patch row i of crop b -> x[b*Tn + img_pos - P + i].  The CLS row lands on the <im_start> slot
         # (img_pos - 1 >= P) and is overwritten by the embedding splice below.
         ops.gemm(ct, self.w.mm_w, out=x, bias=self.w.mm_b, rows_per_group=S, group_stride=Tn, group_offset=img_pos - 1 - P)
-        ids_new = input_ids[:, P:].contiguous() if P else input_ids.contiguous()
+        ids_new = (input_ids[:, P:] if P else input_ids).contiguous().to(self.dev, non_blocking=True)
         ops.embed_splice(ids_new, self.w.embed, x, img_pos - P, n_img)
         if P:
             if self._prefix_slots < B:                  # slots that do not hold the prefix rows yet
@@ -476,8 +478,20 @@ class VSMEngine(LlamaClipCore):
             out["pred_logits"], out["scores"], out["pred_boxes"] = self.owl_heads(fmap, det_q, crop_of_loc)
         return out
 
+    def finish(self, out):
+        """resolve a deferred inference(): the one host sync (greedy argmax of the answer rows vs the draft)"""
+        if out.get("verified") is None:
+            am, draft, B = out.pop("_am"), out.pop("_draft"), out["n_crops"]
+            am = am.view(B, -1).cpu()
+            ok = [bool((am[b] == draft).all()) for b in range(B)] if not out.pop("_forced") else [True] * B
+            self.last_argmax = am
+            self.stats["fallback"] += sum(1 for o in ok if not o)
+            self.stats["verified"] += sum(1 for o in ok if o)
+            out["verified"] = ok
+        return out
+
     def inference(self, images, images_clip, prompt_ids, draft_ids, eos_token_id=2, max_new_tokens=100, mode="detection",
-                  forced_ids=None):
+                  forced_ids=None, defer=False):
         """== VSMForCausalLM.inference (VSM.py:438-553) for a batch of crops sharing one prompt length.
         prompt_ids [B,Lp]; draft_ids [g] = the expected greedy answer incl. EOS (e.g. tokenizer("Sure, [LOC] .")+EOS).
         `forced_ids` (tests / synthetic weights only) forces the emitted tokens like a logits processor would, in which
@@ -485,26 +499,25 @@ class VSMEngine(LlamaClipCore):
         c = self.cfg
         B, Lp = prompt_ids.shape
         g = len(draft_ids)
-        draft = torch.as_tensor(draft_ids, dtype=torch.int64, device=self.dev)
-        ids = torch.cat([prompt_ids.to(self.dev), draft[:-1].unsqueeze(0).expand(B, -1)], dim=1).contiguous()
+        draft = torch.as_tensor(draft_ids, dtype=torch.int64)
+        ids = torch.cat([prompt_ids.cpu(), draft[:-1].unsqueeze(0).expand(B, -1)], dim=1).contiguous()      # host tensor
         x, T, img_pos = self.prefill(ids, images_clip)
         n_img = c.clip_tokens
         # rows that predict answer token j (j = 0..g-1): original index Lp-1+j -> spliced row +255
         pred_rows = torch.tensor([self.x_row(b, (Lp - 1 + j) + n_img - 1) for b in range(B) for j in range(g)], dtype=torch.int64, device=self.dev)
         hn, am, logits = self._logits_rows(x, pred_rows)
-        am = am.view(B, g).cpu()
-        ok = [bool((am[b] == draft.cpu()).all()) for b in range(B)] if forced_ids is None else [True] * B
-        self.last_argmax = am
         self.last_logits = logits.view(B, g, -1)
-        out_ids = [torch.cat([prompt_ids[b].cpu(), draft.cpu()]) for b in range(B)]
-        # crops whose greedy answer deviates from the draft are flagged; the caller re-runs them with exact step-wise
-        # greedy decoding (VSMEngine.generate) so emitted ids are always the reference's greedy ids
-        self.stats["fallback"] += sum(1 for o in ok if not o)
-        self.stats["verified"] += sum(1 for o in ok if o)
+        d_host = torch.as_tensor(draft_ids, dtype=torch.int64)
+        out_ids = [torch.cat([prompt_ids[b].cpu(), d_host]) for b in range(B)]
+        # crops whose greedy answer deviates from the draft are flagged (finish()); the caller re-runs them with exact
+        # step-wise greedy decoding (VSMEngine.generate) so emitted ids are always the reference's greedy ids.  With
+        # defer=True nothing here waits for the GPU: the caller can prepare the next chunk while this one runs.
+        pending = dict(verified=None, _am=am, _draft=d_host, _forced=forced_ids is not None, n_crops=B)
         if mode == "vqa":
-            return dict(output_ids=out_ids, verified=ok, n_crops=B)
+            pending["output_ids"] = out_ids
+            return pending if defer else self.finish(pending)
         rows, crop_of_loc = [], []
-        d_cpu = draft.cpu().tolist()
+        d_cpu = d_host.tolist()
         for b in range(B):
             for j, tok in enumerate(d_cpu):
                 if tok == c.loc_token_idx:
@@ -513,8 +526,9 @@ class VSMEngine(LlamaClipCore):
         if not rows:
             raise RuntimeError("no [LOC] token generated (reference: IndexError at visual_search.py:209-211)")
         out = self._heads(x, T, rows, crop_of_loc, images, mode)
-        out["output_ids"], out["verified"], out["n_crops"] = out_ids, ok, B
-        return out
+        out["output_ids"] = out_ids
+        out.update(pending)
+        return out if defer else self.finish(out)
 
     def generate(self, prompt_ids, images_clip, max_new_tokens=100, eos_token_id=2, forced_ids=None):
         """Exact greedy decoding for ONE sequence on the fused-QKV cache (reference: HF generate, use_cache=False —

@@ -96,26 +96,45 @@ class GpuImagePipeline:
         self.clip_size, self.owl_size = clip_size, owl_size
         self.coefs = _DevCoefs(device)
         self._tmp = None
-        self._pin = self._pin_np = self._pin_evt = None
+        self._ring = []              # pinned staging slots: [tensor, numpy view, event of the last copy out of it]
+        self._ring_next = 0
+        self._copy_stream = None
+
+    RING_SLOTS = 8
 
     def upload(self, pil_img):
-        """PIL RGB image -> resident uint8 [H, W, 3] device tensor (one H2D per search image) through a reusable pinned
-        staging buffer (page-locking a fresh buffer per image costs more than the copy itself)"""
+        """PIL RGB image -> resident uint8 [H, W, 3] device tensor (one H2D per search image).
+
+        The copy runs on a side stream out of a small ring of reusable pinned staging buffers (page-locking a fresh buffer
+        per image costs more than the copy itself) and the compute stream waits for it with an event, never the host: the
+        host only blocks when the ring wraps onto a slot whose copy has not finished.  That lets the caller convert the
+        next image while earlier crops are being evaluated (VSM._run pipelines chunks this way)."""
         if pil_img.mode != "RGB":
             pil_img = pil_img.convert("RGB")
         w, h = pil_img.size
         n = h * w * 3
-        if self._pin is None or self._pin.numel() < n:
-            self._pin = torch.empty(max(n, 4 << 20), dtype=torch.uint8).pin_memory()
-            self._pin_np = self._pin.numpy()
-            self._pin_evt = None
-        if self._pin_evt is not None:
-            self._pin_evt.synchronize()           # previous async copy out of the staging buffer has finished
-        np.copyto(self._pin_np[:n].reshape(h, w, 3), np.asarray(pil_img))
-        dev = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)
-        dev.copy_(self._pin[:n].view(h, w, 3), non_blocking=True)
-        self._pin_evt = torch.cuda.Event()
-        self._pin_evt.record()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        if len(self._ring) < self.RING_SLOTS:
+            self._ring.append([None, None, None])
+        k = self._ring_next % len(self._ring)
+        self._ring_next += 1
+        slot = self._ring[k]
+        if slot[2] is not None:
+            slot[2].synchronize()                 # the previous copy out of this slot has finished
+        if slot[0] is None or slot[0].numel() < n:
+            slot[0] = torch.empty(max(n, 4 << 20), dtype=torch.uint8).pin_memory()
+            slot[1] = slot[0].numpy()
+        np.copyto(slot[1][:n].reshape(h, w, 3), np.asarray(pil_img))
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._copy_stream):
+            dev = torch.empty((h, w, 3), dtype=torch.uint8, device=self.device)     # from the copy stream's pool
+            dev.copy_(slot[0][:n].view(h, w, 3), non_blocking=True)
+            evt = torch.cuda.Event()
+            evt.record(self._copy_stream)
+        dev.record_stream(main)                   # consumed by kernels on the compute stream
+        main.wait_event(evt)
+        slot[2] = evt
         return dev
 
     def _scratch(self, nbytes):
