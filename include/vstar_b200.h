@@ -86,7 +86,9 @@ int vsb_copy2d_b16(const void* src, long long lds, void* dst, long long ldd, lon
  * with gate/up rows interleaved, wdown [d,inter], ln1/ln2 [d]; rope tables bf16 [max_pos, head_dim/2]; scratch: bf16
  * B*Tn*(2d+inter) elements.  Ragged batches (continuous-batched decode): sequences are LEFT-padded in the cache so that
  * they all end at row past+Tn; positions int32 [B*Tn] gives each new row its RoPE position and k_start int32 [B] the first
- * cache row of each sequence (requires Tn <= 4); both NULL for the aligned case.  8 kernel launches per layer. */
+ * cache row of each sequence (requires Tn <= 4); both NULL for the aligned case.  tail_rows > 0: the caller will read only
+ * the last tail_rows rows of every sequence, so the LAST layer runs attention / o-proj / MLP on those rows only (all other
+ * rows of x are left at their layer n-1 value); 0 = every row.  8 kernel launches per layer. */
 typedef struct {
   const void* ln1;
   const void* wqkv;
@@ -97,7 +99,7 @@ typedef struct {
 } vsb_llama_layer_t;
 int vsb_llama_layers(const vsb_llama_layer_t* layers, int n_layers, void* x, int B, int Tn, int past, void* cache, int Bc, int Tmax,
                      int d, int H, int inter, float rms_eps, const void* rope_cos, const void* rope_sin, const void* positions,
-                     const void* k_start, void* scratch, void* stream);
+                     const void* k_start, int tail_rows, void* scratch, void* stream);
 
 /* softmax(QK^T*scale [+causal]) V, head_dim 64/128; element (b,s,h,d) at base + b*bs + s*rs + h*D + d.
  * HF CLIP/OWL attention (modeling_clip.py:261-329) and Llama attention (modeling_llama.py:199-221). */

@@ -12,6 +12,10 @@
 
 #include <math.h>
 
+int vsb_flash_attn_tc(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_rs, long long k_bs, long long k_rs,
+                      long long v_bs, long long v_rs, long long o_bs, long long o_rs, int B, int H, int Sq, int Sk, int D, int causal,
+                      float scale, cudaStream_t stream);
+
 #define VSB_TRY(call)          \
   do {                         \
     int _r = (call);           \
@@ -20,7 +24,7 @@
 
 extern "C" int vsb_llama_layers(const vsb_llama_layer_t* layers, int n_layers, void* x, int B, int Tn, int past, void* cache, int Bc,
                                 int Tmax, int d, int H, int inter, float rms_eps, const void* rope_cos, const void* rope_sin,
-                                const void* positions, const void* k_start, void* scratch, void* stream) {
+                                const void* positions, const void* k_start, int tail_rows, void* scratch, void* stream) {
   VSB_CHECK_ARG(layers && x && cache && rope_cos && rope_sin && scratch, "vsb_llama_layers: null pointer");
   VSB_CHECK_ARG(n_layers > 0 && B > 0 && Tn > 0 && past >= 0 && d > 0 && H > 0 && inter > 0, "vsb_llama_layers: bad shape");
   VSB_CHECK_ARG(B <= Bc && past + Tn <= Tmax, "vsb_llama_layers: B=%d Tn=%d past=%d exceed the cache [%d, %d]", B, Tn, past, Bc, Tmax);
@@ -34,12 +38,31 @@ extern "C" int vsb_llama_layers(const vsb_llama_layer_t* layers, int n_layers, v
   bf16* h = reinterpret_cast<bf16*>(scratch);          // [rows, d]
   bf16* attn = h + rows * d;                            // [rows, d]
   bf16* gu = attn + rows * d;                           // [rows, inter]
+  // tail mode: the caller consumes only the last `tail_rows` rows of every sequence (answer-predicting rows and the [LOC]
+  // row of the guided search).  K/V of the last layer are needed by nobody else, so that layer runs its attention,
+  // o-projection and MLP over B*tail rows only (same kernels, same per-row arithmetic => same values on those rows).
+  const bool tail = tail_rows > 0 && 2 * tail_rows <= Tn && k_start == nullptr && (hd == 64 || hd == 128);
   for (int li = 0; li < n_layers; ++li) {
     const vsb_llama_layer_t& L = layers[li];
     bf16* cl = reinterpret_cast<bf16*>(cache) + (long long)li * Bc * Tmax * ld;       // [Bc*Tmax, 3d]
     VSB_TRY(vsb_rmsnorm_bf16(xb, d, L.ln1, h, d, (int)rows, d, rms_eps, stream));
     VSB_TRY(vsb_gemm_bf16(h, d, L.wqkv, d, cl, ld, (int)rows, 3 * d, d, nullptr, nullptr, 0, VSB_EPI_NONE, 0, Tn, Tmax, past, stream));
     VSB_TRY(vsb_rope_bf16(cl, ld, (int)rows, Tn, H, hd, past, rope_cos, rope_sin, positions, Tmax, past, stream));
+    if (tail && li == n_layers - 1) {
+      const long long trows = (long long)B * tail_rows;
+      bf16* xt = attn + trows * d;                                                     // compact copy of the tail rows of x
+      const int q0 = past + Tn - tail_rows;
+      VSB_TRY(vsb_flash_attn_tc(cl + (long long)q0 * ld, cl + d, cl + 2 * d, attn, (long long)Tmax * ld, ld, (long long)Tmax * ld, ld,
+                                (long long)Tmax * ld, ld, (long long)tail_rows * d, d, B, H, tail_rows, past + Tn, hd, 1, scale,
+                                reinterpret_cast<cudaStream_t>(stream)));
+      VSB_TRY(vsb_copy2d_b16(xb + (long long)(Tn - tail_rows) * d, (long long)Tn * d, xt, (long long)tail_rows * d, B, tail_rows * d, stream));
+      VSB_TRY(vsb_gemm_bf16(attn, d, L.wo, d, xt, d, (int)trows, d, d, nullptr, xt, d, VSB_EPI_NONE, 0, 0, 0, 0, stream));
+      VSB_TRY(vsb_rmsnorm_bf16(xt, d, L.ln2, h, d, (int)trows, d, rms_eps, stream));
+      VSB_TRY(vsb_gemm_bf16(h, d, L.wgu, d, gu, inter, (int)trows, 2 * inter, d, nullptr, nullptr, 0, VSB_EPI_SWIGLU, 0, 0, 0, 0, stream));
+      VSB_TRY(vsb_gemm_bf16(gu, inter, L.wdown, inter, xt, d, (int)trows, d, inter, nullptr, xt, d, VSB_EPI_NONE, 0, 0, 0, 0, stream));
+      VSB_TRY(vsb_copy2d_b16(xt, (long long)tail_rows * d, xb + (long long)(Tn - tail_rows) * d, (long long)Tn * d, B, tail_rows * d, stream));
+      break;
+    }
     if (k_start != nullptr)
       VSB_TRY(vsb_attn_decode_bf16(cl + (long long)past * ld, cl + d, cl + 2 * d, attn, (long long)Tmax * ld, ld, (long long)Tmax * ld, ld,
                                    (long long)Tmax * ld, ld, (long long)Tn * d, d, B, H, Tn, past + Tn, hd, 1, scale, k_start, stream));

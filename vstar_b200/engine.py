@@ -17,6 +17,7 @@ torch is used for device memory, streams and a few index/slice views only.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -202,6 +203,7 @@ class LlamaClipCore:
         self.stats = dict(verified=0, fallback=0, prefix_shared=0)
         # shared-prefix KV (see prefill): the text before <im_start> is the same for every crop
         self.prefix_cache = True
+        self.tail_only = os.environ.get("VSB_TAIL_ONLY", "1") != "0"    # last layer over the consumed rows only (draft-verify path)
         self._prefix_ids = None          # tuple of token ids
         self._prefix_kv = None           # [n_layers, P, 3d] snapshot of the cache rows of that prefix
         self._prefix_slots = 0           # cache slots whose rows 0..P currently hold it
@@ -255,7 +257,7 @@ class LlamaClipCore:
             self._prefix_slots = 0
         return self._cache
 
-    def _llm_layers(self, x, B, Tn, past, Tmax, positions=None, k_start=None, cache_row_offset=0):
+    def _llm_layers(self, x, B, Tn, past, Tmax, positions=None, k_start=None, cache_row_offset=0, tail_rows=0):
         """Run all decoder layers over the Tn new rows per sequence in x [B*Tn, d] (in place on the residual stream).
         Fused q|k|v rows live in the per-layer cache [B, Tmax, 3d] at positions past..past+Tn.  One native call
         (csrc/llama_layers.cu) sequences the 8 kernels of every layer: RMSNorm, QKV GEMM writing cache rows, RoPE in
@@ -267,7 +269,7 @@ class LlamaClipCore:
         scratch = torch.empty((B * Tn * (2 * c.hidden + c.intermediate),), dtype=BF, device=self.dev)
         return ops.llama_layers(self._layer_table, len(self.w.layers), x, B, Tn, past, self._cache, Bc, Tm, c.hidden, c.n_heads,
                                 c.intermediate, c.rms_eps, self.w.rope_cos, self.w.rope_sin, scratch, positions=positions,
-                                k_start=k_start, cache_row_offset=cache_row_offset)
+                                k_start=k_start, cache_row_offset=cache_row_offset, tail_rows=tail_rows)
 
     def _logits_rows(self, x, rows):
         """final RMSNorm + lm_head on selected rows of the residual stream -> (hidden [n,d], argmax [n], logits fp32 [n,V])"""
@@ -283,8 +285,9 @@ class LlamaClipCore:
         assert pos >= self._P, "position inside the shared prefix: its rows are not recomputed"
         return b * self._Tn + pos - self._P
 
-    def prefill(self, input_ids, images_clip):
+    def prefill(self, input_ids, images_clip, tail_rows=0):
         """input_ids int64 [B, L] (same L and same image position for the whole batch), images_clip [B,3,224,224] bf16.
+        tail_rows > 0: the caller reads only the last tail_rows positions of every crop (see vsb_llama_layers).
         Returns (x, T, img_pos): the residual stream (pre final norm) of the rows that were computed, the spliced length T
         and the image position.  Use x_row(b, pos) to address x.
 
@@ -331,7 +334,7 @@ class LlamaClipCore:
                 self._cache[:, self._prefix_slots:B, :P].copy_(self._prefix_kv[:, None])
                 self._prefix_slots = B
             self.stats["prefix_shared"] += B
-        self._llm_layers(x, B, Tn, P, self.max_tokens)
+        self._llm_layers(x, B, Tn, P, self.max_tokens, tail_rows=tail_rows if self.tail_only else 0)
         if not P and self.prefix_cache and img_pos >= 2 and self._prefix_ids is None:
             head = input_ids[:, :img_pos - 1]
             if bool((head == head[0]).all()):
@@ -501,7 +504,7 @@ class VSMEngine(LlamaClipCore):
         g = len(draft_ids)
         draft = torch.as_tensor(draft_ids, dtype=torch.int64)
         ids = torch.cat([prompt_ids.cpu(), draft[:-1].unsqueeze(0).expand(B, -1)], dim=1).contiguous()      # host tensor
-        x, T, img_pos = self.prefill(ids, images_clip)
+        x, T, img_pos = self.prefill(ids, images_clip, tail_rows=g)      # only the g answer-predicting rows are read below
         n_img = c.clip_tokens
         # rows that predict answer token j (j = 0..g-1): original index Lp-1+j -> spliced row +255
         pred_rows = torch.tensor([self.x_row(b, (Lp - 1 + j) + n_img - 1) for b in range(B) for j in range(g)], dtype=torch.int64, device=self.dev)
