@@ -325,6 +325,8 @@ def run_b200(args):
     peak_tf, peak_hbm, peak_src = peaks()
     # executed FLOPs per crop: BASELINE.md §3's 5.00e12 minus the 7B linear work of the prefix rows that are not recomputed
     flops_per_crop = FLOPS_PER_CROP - 2.0 * engine._P * 6.476e9
+    if engine.tail_only and not args.tiny:      # last layer: o-proj + MLP only on the 5 consumed rows of each crop
+        flops_per_crop -= 2.0 * (320 - engine._P - 5) * (cfg.hidden * cfg.hidden + 3 * cfg.hidden * cfg.intermediate)
     value = dev_crops / (dev_ms / 1e3)
     e2e = e2e_crops / (e2e_ms / 1e3)
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
@@ -342,7 +344,8 @@ def run_b200(args):
                      "how": "sum(2*M*N*K) / sum(CUDA-event duration) over every GEMM launch of the timed region; peak = " + peak_src,
                      "whole_path_frac": value / world * flops_per_crop / (peak_tf * 1e12),
                      "whole_path_note": ("crops/s/GPU x %.2f TFLOP/crop executed / peak (BASELINE.md §3 counts 5.00 TFLOP/crop at T=320; "
-                                         "%d constant prefix rows per crop are served from the shared-prefix KV snapshot)"
+                                         "%d constant prefix rows per crop are served from the shared-prefix KV snapshot, and the last "
+                                         "decoder layer runs o-proj/MLP on the 5 consumed rows only)"
                                          % (flops_per_crop / 1e12, engine._P))},
         "crops_per_step": dev_crops // args.steps, "load_s": load_s,
         "draft_verify": engine.stats,

@@ -74,7 +74,7 @@ def llama_layers(table, n_layers, x, B, Tn, past, cache, Bc, Tmax, d, H, inter, 
         assert t is None or (t.dtype == torch.int32 and t.is_contiguous() and t.is_cuda)
     assert positions is None or positions.numel() == B * Tn
     assert k_start is None or k_start.numel() == B
-    _lib.launches += 8 * n_layers
+    _lib.launches += 8 * n_layers + (2 if (tail_rows > 0 and 2 * tail_rows <= Tn and k_start is None) else 0)
     call("vsb_llama_layers", table, n_layers, x.data_ptr(), B, Tn, past, cache.data_ptr() + cache_row_offset * 3 * d * 2, Bc, Tmax, d, H,
          inter, float(eps), rope_cos.data_ptr(), rope_sin.data_ptr(), _p(positions), _p(k_start), int(tail_rows), scratch.data_ptr(),
          _stream())
