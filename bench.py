@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--tiny", action="store_true", help="tiny model (debug only; not a valid bench)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--attn-impl", type=int, default=0, help="A/B switch for vsb_attn_set_impl (0 = production dispatch)")
+    ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around the timed resident steps (for ncu)")
     ap.add_argument("--no-prefix-cache", action="store_true",
                     help="recompute the K/V rows of the constant text prefix (system prompt before <im_start>) for every crop")
     return ap.parse_args()
@@ -112,7 +113,10 @@ def cpu_reference_sample(llama_layers=2, tiny=False):
         n_threads = len(os.sched_getaffinity(0))
     except Exception:
         n_threads = os.cpu_count() or 1
-    torch.set_num_threads(max(1, n_threads))
+    # measured on the pool's boxes: 64 threads -> 12 s per crop, 128 SMT threads -> 180 s (oversubscribed fp32 GEMMs); the
+    # baseline uses the faster setting and reports the thread count it used
+    n_threads = min(max(1, n_threads), 64)
+    torch.set_num_threads(n_threads)
     cfg = tiny_config() if tiny else VSMConfig()
     full_layers = cfg.n_layers
     run_layers = min(llama_layers, full_layers)
@@ -247,7 +251,7 @@ def run_b200(args):
     weights = VSMWeights(cfg, lambda n, _s=synth.state_dict_shapes(cfg): synth.synthetic_tensor(n, _s[n], seed=1234, device="cuda"))
     engine = VSMEngine(weights, max_tokens=384)
     engine.prefix_cache = not args.no_prefix_cache
-    prompt, ans = synth.synthetic_prompt(cfg, n_text=60, seed=0)
+    prompt, ans = synth.synthetic_prompt(cfg, n_text=60, seed=0, im_start_index=None if args.tiny else 37)
 
     class BenchVSM(VSM):
         """synthetic tokenisation (no sentencepiece model offline): fixed 60-id prompt, forced 5-id answer"""
@@ -312,7 +316,11 @@ def run_b200(args):
     # GEMM roofline: CUDA events around every tcgen05 GEMM launch of the timed region
     ops.profile_begin()
     launches0 = _lib.launches
+    if args.profile_range:           # `ncu --profile-from-start off`: capture exactly the timed resident steps
+        torch.cuda.profiler.start()
     dev_ms, dev_crops = timed_steps(args.steps, True)
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     launches = _lib.launches - launches0
     gemm_flops, gemm_ms, gemm_n = ops.profile_end()
     clocks = sampler.stop() if rank == 0 else None

@@ -507,17 +507,23 @@ def test_llama_layers_native_runner(ops):
     for a, b in zip(outs[0], outs[1]):
         assert torch.equal(a, b)
     assert float(outs[0][0].float().abs().max()) > 0 and torch.isfinite(outs[0][1].float()).all()
-    # tail mode: the last layer runs attention / o-proj / MLP over the last 5 rows of every sequence only; those rows must be
-    # bit-identical to the full computation, and the cache (K/V of every row, every layer) too
+    # tail mode: the last layer runs attention / o-proj / MLP over the last rows of every sequence only.  The cache (K/V of
+    # every row, every layer) must be bit-identical; the tail rows are bit-identical when the compact GEMMs run on the same
+    # tcgen05 kernels as the full pass (more than 16 rows: B * tail = 18) and equal to bf16 rounding when the few rows take
+    # the decode GEMM kernels (B * tail = 10), whose k order differs.
     cache_f = torch.zeros(nl, B, Tmax, 3 * d, dtype=BF, device="cuda")
-    cache_t = torch.zeros_like(cache_f)
     xf = native_stack(rnd(B * 70, d, seed=110).clone(), cache_f, 70, 0)
-    xt = rnd(B * 70, d, seed=110).clone()
     scratch = torch.empty(B * 70 * (2 * d + inter), dtype=BF, device="cuda")
-    ops.llama_layers(table, nl, xt, B, 70, 0, cache_t, B, Tmax, d, H, inter, 1e-6, cos_t, sin_t, scratch, tail_rows=5)
-    torch.cuda.synchronize()
-    assert torch.equal(cache_f, cache_t)
-    assert torch.equal(xf.view(B, 70, d)[:, -5:], xt.view(B, 70, d)[:, -5:])
-    assert not torch.equal(xf.view(B, 70, d)[:, :-5], xt.view(B, 70, d)[:, :-5])       # the other rows were indeed skipped
+    for tail, exact in ((9, True), (5, False)):
+        cache_t = torch.zeros_like(cache_f)
+        xt = rnd(B * 70, d, seed=110).clone()
+        ops.llama_layers(table, nl, xt, B, 70, 0, cache_t, B, Tmax, d, H, inter, 1e-6, cos_t, sin_t, scratch, tail_rows=tail)
+        torch.cuda.synchronize()
+        assert torch.equal(cache_f, cache_t)
+        a, b = xf.view(B, 70, d)[:, -tail:], xt.view(B, 70, d)[:, -tail:]
+        if exact:
+            assert torch.equal(a, b)
+        assert torch.allclose(a.float(), b.float(), rtol=2e-2, atol=2e-2)
+        assert not torch.equal(xf.view(B, 70, d)[:, :-tail], xt.view(B, 70, d)[:, :-tail])   # the other rows were indeed skipped
     with pytest.raises(Exception):
         native_stack(rnd(B * 30, d, seed=112), torch.zeros(nl, B, Tmax, 3 * d, dtype=BF, device="cuda"), 30, 70)    # exceeds Tmax

@@ -536,21 +536,12 @@ extern "C" int vsb_flash_attn_bf16(const void* q, const void* k, const void* v, 
   p.scale_log2 = scale * 1.4426950408889634f;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (D == 64) {
-    // 128 query rows per CTA (2 m16 tiles per warp) once there are enough rows to fill them
-    if (false && Sq > 64) {   // MT=2 measured SLOWER on B200 (218 regs -> half the occupancy): 155 vs 182 TFLOP/s on OWL shapes
-      constexpr int BMq = 128;
-      const int smem = (BMq + 4 * FA_BN) * 64 * 2;
-      static bool set64b = false;
-      if (!set64b) { VSB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set64b = true; }
-      dim3 grid((Sq + BMq - 1) / BMq, H, B);
-      flash_attn_kernel<64, 2><<<grid, 128, smem, st>>>(p);
-    } else {
-      const int smem = (64 + 4 * FA_BN) * 64 * 2;
-      static bool set64 = false;
-      if (!set64) { VSB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set64 = true; }
-      dim3 grid((Sq + 63) / 64, H, B);
-      flash_attn_kernel<64, 1><<<grid, 128, smem, st>>>(p);
-    }
+    // (a 128-query-row variant, 2 m16 tiles per warp, measured slower on B200: 218 registers halve the occupancy)
+    const int smem = (64 + 4 * FA_BN) * 64 * 2;
+    static bool set64 = false;
+    if (!set64) { VSB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set64 = true; }
+    dim3 grid((Sq + 63) / 64, H, B);
+    flash_attn_kernel<64, 1><<<grid, 128, smem, st>>>(p);
   } else {
     const int smem = (64 + 4 * FA_BN) * 128 * 2;
     static bool set128 = false;

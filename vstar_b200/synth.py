@@ -170,15 +170,17 @@ def synthetic_tensor(name, shape, seed=1234, dtype=torch.float32, device="cpu"):
     return t.to(dtype)
 
 
-def synthetic_prompt(cfg: VSMConfig, n_text=60, seed=0, answer=True):
+def synthetic_prompt(cfg: VSMConfig, n_text=60, seed=0, answer=True, im_start_index=None):
     """Fixed-length synthetic prompt: BOS, ids, <im_start>, -200,
-    <im_end>, ids; optional forced answer [a, b, LOC, c, EOS]."""
+    <im_end>, ids; optional forced answer [a, b, LOC, c, EOS].  im_start_index places <im_start> (index 37 =
+    BOS + 36 ids, the length of the llava_v1 system prompt + "USER:"); default min(37, n_text // 2) as in the goldens."""
     g = torch.Generator().manual_seed(777 + seed)
     hi = min(cfg.vocab - 24, 31990)   # never draws [LOC] / <im_start> / <im_end>
     ids = torch.randint(3, hi, (n_text,), generator=g)
     ids[0] = 1
     im_start, im_end = cfg.vocab - 2, cfg.vocab - 1
-    p = min(37, n_text // 2)
+    p = min(37, n_text // 2) if im_start_index is None else int(im_start_index)
+    assert 1 <= p <= n_text - 3
     ids[p], ids[p + 1], ids[p + 2] = im_start, IMAGE_TOKEN_INDEX, im_end
     ans = torch.tensor([int(ids[3]), int(ids[4]), cfg.loc_token_idx, int(ids[5]), 2])
     return ids.unsqueeze(0), ans
