@@ -182,9 +182,9 @@ class StubVSM:
     """Deterministic stand-in for visual_search.VSM: outputs depend only on the
     crop's pixels (so they are pure functions of the crop, like the real VSM)."""
 
-    def __init__(self, conf_peak_bbox=None, weak_every=0):
+    def __init__(self, hot=None):
         self.calls = []
-        self.weak_every = weak_every
+        self.hot = hot
 
     def inference(self, image, question, mode="segmentation"):
         arr = np.asarray(image, dtype=np.uint8)
@@ -201,6 +201,10 @@ class StubVSM:
             return hm
         logits = torch.from_numpy(rng.uniform(0.0, 0.45, (2304, 1)).astype(np.float32))
         boxes = torch.from_numpy(rng.uniform(0.1, 0.9, (2304, 4)).astype(np.float32))
+        if self.hot == "root" and min(w, h) >= 600:
+            logits[100, 0], logits[7, 0], logits[2000, 0] = 0.9, 0.7, 0.6
+        if self.hot == "small" and min(w, h) <= 300:
+            logits[55, 0] = 0.8
         return boxes, logits, hm
 
 
@@ -208,20 +212,22 @@ def trajectory(search_path):
     return np.array([st["bbox"] for st in search_path], dtype=np.int64)
 
 
-def case_search(tag, img_seed, w, h, smallest, **kw):
+def case_search(tag, img_seed, w, h, smallest, hot=None, **kw):
     print(f"[golden] search case {tag}")
     import visual_search as RVS  # the reference module
     img = synth_image(img_seed, w, h)
-    stub = StubVSM()
+    stub = StubVSM(hot)
     fs, pl, ok, av = RVS.visual_search(stub, img, "mug", None, smallest, **kw)
     ref_calls = list(stub.calls)
-    stub2 = StubVSM()
+    stub2 = StubVSM(hot)
     fs2, pl2, ok2, av2, path2 = O.visual_search(stub2, img, "mug", None, smallest, **kw)
     assert ref_calls == stub2.calls
     assert pl == pl2 and ok == ok2 and fs["bbox"] == fs2["bbox"]
     assert torch.equal(fs["detection_result"], fs2["detection_result"])
+    assert (av is None) == (av2 is None) and (av is None or torch.equal(av, av2))
     np.savez_compressed(os.path.join(GOLDEN_DIR, f"search_{tag}.npz"), img_seed=img_seed, w=w, h=h, smallest=smallest,
-                        kw=json.dumps(kw), calls=np.array([(c[0], c[1], {"detection": 0, "vqa": 1, "segmentation": 2}[c[2]])
+                        kw=json.dumps(kw), hot=str(hot), all_valid_boxes=(av.numpy() if av is not None else np.zeros((0, 4), np.float32)),
+                        has_all_valid=int(av is not None), calls=np.array([(c[0], c[1], {"detection": 0, "vqa": 1, "segmentation": 2}[c[2]])
                                                            for c in ref_calls], dtype=np.int64),
                         trajectory=trajectory(path2), path_length=pl, success=int(ok), final_bbox=np.array(fs["bbox"]),
                         detection_result=fs["detection_result"].numpy())
@@ -381,7 +387,21 @@ def case_bench_eval():
     print("   ", {t: len(v) for t, v in res.items()}, "samples;", sum(len(r["search_result"]) for v in res.values() for r in v), "search results")
 
 
+def search_edge_cases():
+    """termination / selection branches of visual_search() (visual_search.py:399-413, :428-431, :497-512)"""
+    case_search("edge_root_hit", img_seed=24, w=1280, h=960, smallest=224, hot="root")          # success at the root, 3 valid boxes
+    case_search("edge_deep_hit", img_seed=25, w=1100, h=1000, smallest=224, hot="small")        # success below the root
+    case_search("edge_tiny", img_seed=26, w=200, h=150, smallest=224)                           # root is already the smallest unit
+    case_search("edge_tiny_unsure", img_seed=26, w=200, h=150, smallest=224, confidence_low=0.9)  # nothing passes confidence_low
+    case_search("edge_wide", img_seed=27, w=2000, h=420, smallest=224, confidence_high=2.0)      # 4x1 splits (h/w <= 0.5)
+    case_search("edge_odd", img_seed=28, w=1001, h=777, smallest=251, confidence_high=2.0)       # sizes not divisible by the grid
+
+
 def main():
+    if os.environ.get("GOLDEN_ONLY") == "search_edges":
+        assert ref_shims.reference_available()
+        ref_shims.install(*hf_cfgs(O.tiny_config()))
+        return search_edge_cases()
     if os.environ.get("GOLDEN_ONLY") == "bench_eval":
         assert ref_shims.reference_available()
         ref_shims.install(*hf_cfgs(O.tiny_config()))
@@ -401,6 +421,7 @@ def main():
     case_search("stub_default", img_seed=22, w=1500, h=700, smallest=224)
     case_search("stub_weakcue", img_seed=23, w=900, h=1900, smallest=300, confidence_high=2.0,
                 target_cue_threshold=50.0, target_cue_threshold_minimum=40.0)
+    search_edge_cases()
     case_search_model(m, sd, cfg, "a", img_seed=31, w=640, h=512, smallest=200, confidence_high=2.0,
                       target_cue_threshold=-1e9, target_cue_threshold_minimum=-1e9)
     case_vqa("a", img_seed=41)

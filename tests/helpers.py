@@ -41,9 +41,12 @@ class NumpyScorer:
 
 
 class StubVSM:
-    # identical to oracle/make_golden.py:StubVSM (pure function of crop pixels)
-    def __init__(self):
+    # identical to oracle/make_golden.py:StubVSM (pure function of crop pixels).  hot: None = detection logits stay below
+    # 0.45 (never confident); "root" = crops with min side >= 600 get three confident boxes (0.9 / 0.7 / 0.6); "small" = crops
+    # with min side <= 300 get one confident box (0.8)
+    def __init__(self, hot=None):
         self.calls = []
+        self.hot = hot
 
     def inference(self, image, question, mode="segmentation"):
         arr = np.asarray(image, dtype=np.uint8)
@@ -60,6 +63,10 @@ class StubVSM:
             return hm
         logits = torch.from_numpy(rng.uniform(0.0, 0.45, (2304, 1)).astype(np.float32))
         boxes = torch.from_numpy(rng.uniform(0.1, 0.9, (2304, 4)).astype(np.float32))
+        if self.hot == "root" and min(w, h) >= 600:
+            logits[100, 0], logits[7, 0], logits[2000, 0] = 0.9, 0.7, 0.6
+        if self.hot == "small" and min(w, h) <= 300:
+            logits[55, 0] = 0.8
         return boxes, logits, hm
 
 

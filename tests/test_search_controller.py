@@ -15,13 +15,29 @@ from vstar_b200 import visual_search as VS
 G = os.path.join(os.path.dirname(__file__), "golden")
 
 
-@pytest.mark.parametrize("tag", ["stub_3lvl", "stub_default", "stub_weakcue"])
+EDGE_TAGS = ["edge_root_hit", "edge_deep_hit", "edge_tiny", "edge_tiny_unsure", "edge_wide", "edge_odd"]
+
+
+def golden_stub(g):
+    hot = str(g["hot"]) if "hot" in g.files else "None"
+    return StubVSM(None if hot == "None" else hot)
+
+
+@pytest.mark.parametrize("tag", ["stub_3lvl", "stub_default", "stub_weakcue"] + EDGE_TAGS)
 def test_trajectory_matches_reference(tag):
+    """trajectories, VSM call sequences and return values of the REAL reference visual_search(); the edge_* cases cover its
+    termination / selection branches: confident hit at the root with several valid boxes (visual_search.py:404-410), hit
+    below the root (:411), root already the smallest unit (:416-417), nothing above confidence_low (:497-512), 4x1 splits
+    and sizes the 2x2 grid does not divide (:234-253)"""
     g = np.load(os.path.join(G, f"search_{tag}.npz"))
     img = synth_image(int(g["img_seed"]), int(g["w"]), int(g["h"]))
     kw = json.loads(str(g["kw"]))
-    stub = StubVSM()
+    stub = golden_stub(g)
     fs, pl, ok, av, st = VS.visual_search(stub, img, "mug", None, int(g["smallest"]), scorer=NumpyScorer(), return_state=True, **kw)
+    if "has_all_valid" in g.files:
+        assert (av is not None) == bool(int(g["has_all_valid"]))
+        if av is not None:
+            assert np.array_equal(av.numpy(), g["all_valid_boxes"])
     assert np.array_equal(np.array([s["bbox"] for s in st.search_path]), g["trajectory"])
     assert np.array_equal(np.array(stub.calls), g["calls"])
     assert pl == int(g["path_length"]) and int(ok) == int(g["success"])

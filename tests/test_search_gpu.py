@@ -14,13 +14,17 @@ G = os.path.join(os.path.dirname(__file__), "golden")
 BF = torch.bfloat16
 
 
-@pytest.mark.parametrize("tag", ["stub_3lvl", "stub_default", "stub_weakcue"])
+@pytest.mark.parametrize("tag", ["stub_3lvl", "stub_default", "stub_weakcue", "edge_root_hit", "edge_deep_hit", "edge_tiny",
+                                 "edge_tiny_unsure", "edge_wide", "edge_odd"])
 def test_cuda_scorer_trajectory(tag):
     from vstar_b200 import visual_search as VS
     g = np.load(os.path.join(G, f"search_{tag}.npz"))
     img = synth_image(int(g["img_seed"]), int(g["w"]), int(g["h"]))
     kw = json.loads(str(g["kw"]))
-    fs, pl, ok, av, st = VS.visual_search(StubVSM(), img, "mug", None, int(g["smallest"]), return_state=True, **kw)
+    hot = str(g["hot"]) if "hot" in g.files else "None"
+    fs, pl, ok, av, st = VS.visual_search(StubVSM(None if hot == "None" else hot), img, "mug", None, int(g["smallest"]),
+                                          return_state=True, **kw)
+    assert int(ok) == int(g["success"])
     assert np.array_equal(np.array([s["bbox"] for s in st.search_path]), g["trajectory"])
     assert pl == int(g["path_length"]) and list(fs["bbox"]) == list(g["final_bbox"])
     # lazily materialised final_heatmap has the reference's [h,w,1] fp32 layout

@@ -115,9 +115,10 @@ class GpuImagePipeline:
         n = h * w * 3
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
-        if len(self._ring) < self.RING_SLOTS:
+        limit = self.RING_SLOTS if n <= (32 << 20) else 2     # huge search images (8192^2 = 201 MB): two staging buffers only
+        if len(self._ring) < limit:
             self._ring.append([None, None, None])
-        k = self._ring_next % len(self._ring)
+        k = self._ring_next % min(len(self._ring), limit)
         self._ring_next += 1
         slot = self._ring[k]
         if slot[2] is not None:
