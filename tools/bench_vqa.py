@@ -108,7 +108,7 @@ def main():
         shp = synth.state_dict_shapes(cfg)
         weights = VSMWeights(cfg, lambda n: synth.synthetic_tensor(n, shp[n], seed=1234, device="cuda"))
         engine = VSMEngine(weights, max_tokens=384)
-        prompt, ans = synth.synthetic_prompt(cfg, n_text=60, seed=0)
+        prompt, ans = synth.synthetic_prompt(cfg, n_text=60, seed=0, im_start_index=37)
 
         class BenchVSM(VSM):
             def _ids(self, question):
