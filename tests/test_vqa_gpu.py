@@ -189,3 +189,50 @@ def test_continuous_batched_decode_matches_single_sequence(setup):
     first = outs[0][0]
     outs2 = eng.generate_batch(reqs, max_new_tokens=4, eos_token_id=first)
     assert outs2[0] == [first] and len(outs2[1]) >= 1
+
+
+def test_model_adapter_runs_the_reference_call_sequence(setup):
+    """`load_pretrained_model`'s model object (LlavaSearchModel) driven exactly like vstar_bench_eval.py:91-103 / :127-160 drives
+    LlavaSearchLlamaForCausalLM: forward with images -> .logits / .past_key_values, forward with past_key_values per option,
+    CrossEntropyLoss over the shifted logits, generate(...) with a stopping criterion"""
+    from vstar_b200.vqa import VQA_LLM
+    V, O, cfg, sd, eng = setup
+    model = VQA_LLM(engine=eng).model
+    rng = np.random.default_rng(11)
+    gen = torch.Generator().manual_seed(3)
+    image = torch.randn(1, 3, 224, 224, generator=gen)
+    crops = torch.randn(2, 3, 224, 224, generator=gen)
+    q = [1] + rng.integers(3, cfg.vocab - 30, 6).tolist() + [-200] + rng.integers(3, cfg.vocab - 30, 5).tolist() + [-300] + \
+        rng.integers(3, cfg.vocab - 30, 3).tolist() + [-300] + rng.integers(3, cfg.vocab - 30, 4).tolist()
+    opts = [rng.integers(3, cfg.vocab - 30, n).tolist() for n in (3, 5, 2)]
+    il, ol = [False], [True, False]
+    qt = torch.tensor([q])
+    assert model.config.vocab_size == cfg.vocab
+    out_q = model(qt, use_cache=True, images=image.half(), object_features=crops.half(), images_long=il, objects_long=ol)
+    T = 32 + 256 + 32 + (len(q) - 3)
+    assert out_q.logits.shape == (1, T, cfg.vocab)
+    losses = []
+    for opt in opts:
+        ot = torch.tensor([opt])
+        o = model(input_ids=ot.cuda(), use_cache=True, attention_mask=torch.ones(1, T + len(opt)), past_key_values=out_q.past_key_values)
+        logits = torch.cat([out_q.logits[:, -1:], o.logits[:, :-1]], 1)
+        losses.append(torch.nn.CrossEntropyLoss()(logits.view(-1, model.config.vocab_size).float(), ot.view(-1).cuda()))
+    losses = torch.stack(losses).cpu()
+    ref_losses, choice = eng.option_losses(q, opts, image.to(BF).cuda(), crops.to(BF).cuda(), il, ol)
+    assert torch.allclose(losses, ref_losses, rtol=1e-3, atol=1e-3) and int(losses.argmin()) == choice
+    # generate: prompt ids are echoed, the criterion sees prompt + new ids and stops the loop
+    seen = []
+    model.eos_token_id = -1                   # random weights: do not let an accidental </s> end the loop
+
+    def criterion(ids, scores):
+        seen.append(ids.shape[1])
+        return ids.shape[1] >= len(q) + 3
+
+    out = model.generate(qt, images=image.half(), object_features=crops.half(), images_long=il, objects_long=ol, do_sample=False,
+                         max_new_tokens=8, use_cache=True, stopping_criteria=[criterion])
+    assert out.shape == (1, len(q) + 3) and out[0, :len(q)].tolist() == q and seen[-1] == len(q) + 3
+    assert out[0, len(q):].tolist() == eng.generate(q, image.to(BF).cuda(), crops.to(BF).cuda(), il, ol, max_new_tokens=3, eos_token_id=-1)
+    with pytest.raises(RuntimeError):          # the cache has been re-prefilled since out_q was produced
+        model(input_ids=torch.tensor([opts[0]]), past_key_values=out_q.past_key_values)
+    with pytest.raises(NotImplementedError):
+        model.generate(qt, images=image.half(), do_sample=True, temperature=0.7)

@@ -168,6 +168,7 @@ class VQAEngine(LlamaClipCore):
         assert T <= self.max_tokens, (T, self.max_tokens)
         self._ensure_cache(1, self.max_tokens)
         self._llm_layers(x, 1, T, 0, self.max_tokens)
+        self.kv_epoch = getattr(self, "kv_epoch", 0) + 1        # handles to an older prefix are stale from here on
         return x
 
     def append_tokens(self, tokens, past):
@@ -184,8 +185,9 @@ class VQAEngine(LlamaClipCore):
         return logits
 
     def generate(self, input_ids, image, object_crops=None, images_long=None, objects_long=None, max_new_tokens=200, eos_token_id=2,
-                 stop_ids=None):
-        """greedy `model.generate(use_cache=True, do_sample=False)` (vstar_bench_eval.py:91-103) -> list of new token ids"""
+                 stop_ids=None, stop_fn=None):
+        """greedy `model.generate(use_cache=True, do_sample=False)` (vstar_bench_eval.py:91-103) -> list of new token ids.
+        stop_ids: stop once the output ends with these ids; stop_fn(new_ids) -> bool: HF-style stopping criterion."""
         x = self.build_embeds(input_ids, image, object_crops, images_long, objects_long)
         T = x.shape[0]
         self.prefill_embeds(x)
@@ -195,7 +197,8 @@ class VQAEngine(LlamaClipCore):
         for _ in range(max_new_tokens):
             nxt = int(ops.argmax_rows(logits)[0][0])
             out.append(nxt)
-            if nxt == eos_token_id or (stop_ids and out[-len(stop_ids):] == list(stop_ids)) or past >= self.max_tokens - 1:
+            if nxt == eos_token_id or (stop_ids and out[-len(stop_ids):] == list(stop_ids)) or past >= self.max_tokens - 1 or \
+                    (stop_fn is not None and stop_fn(out)):
                 break
             logits = self.append_tokens([nxt], past)
             past += 1
@@ -217,6 +220,7 @@ class VQAEngine(LlamaClipCore):
         for b, x in enumerate(xs):
             self._llm_layers(x, 1, lens[b], 0, Tm, cache_row_offset=b * Tm + (Tpad - lens[b]))
             last.append(x[-1:])
+        self.kv_epoch = getattr(self, "kv_epoch", 0) + 1
         hn = ops.rmsnorm(torch.cat(last, 0).contiguous(), self.w.final_norm, self.cfg.rms_eps)
         return ops.gemm(hn, self.w.lm_head, out_dtype=torch.float32), Tpad, lens
 
@@ -298,23 +302,108 @@ class _Proc:
         return {"pixel_values": [_clip_preprocess(image)]}
 
 
+class _ModelConfig:
+    pass
+
+
+class _ModelOutput:
+    def __init__(self, logits, past_key_values):
+        self.logits, self.past_key_values = logits, past_key_values
+
+
+class _Past:
+    """opaque `past_key_values`: the KV rows live in the engine's cache; this records how many are valid and which prefill
+    wrote them (a handle from before a later prefill is rejected instead of silently reading the wrong rows)"""
+
+    def __init__(self, length, epoch):
+        self.length, self.epoch = length, epoch
+
+
+class LlavaSearchModel:
+    """The `model` that load_pretrained_model returns: the part of LlavaSearchLlamaForCausalLM's surface that
+    /root/reference/vstar_bench_eval.py drives (generate(...) at :91-103; forward with images / with past_key_values at
+    :127-152; .config.vocab_size at :157), on the sm_100a engine.  Greedy decoding only (the benchmark uses temperature 0)."""
+
+    def __init__(self, engine: VQAEngine, eos_token_id=2):
+        self.engine = engine
+        self.config = _ModelConfig()
+        self.config.vocab_size = engine.cfg.vocab
+        self.eos_token_id = eos_token_id
+        self.device = torch.device(engine.dev)
+
+    def eval(self):
+        return self
+
+    def cuda(self):
+        return self
+
+    def _px(self, t):
+        if t is None or len(t) == 0:
+            return None
+        return ops.cast_f32_bf16(torch.as_tensor(t).float().to(self.engine.dev).contiguous())
+
+    @torch.inference_mode()
+    def generate(self, input_ids, images=None, object_features=None, images_long=None, objects_long=None, do_sample=False, num_beams=1,
+                 temperature=0, top_p=None, max_new_tokens=200, use_cache=True, stopping_criteria=None, **_):
+        if do_sample or num_beams != 1:
+            raise NotImplementedError("greedy decoding only (vstar_bench_eval.py:196 runs temperature=0, num_beams=1)")
+        ids = input_ids.view(-1).tolist()
+        stop_fn = None
+        if stopping_criteria:
+            def stop_fn(new):
+                full = torch.tensor([ids + list(new)], dtype=torch.int64)
+                return any(bool(sc(full, None)) for sc in stopping_criteria)
+        new = self.engine.generate(ids, self._px(images), self._px(object_features), images_long, objects_long, max_new_tokens,
+                                   self.eos_token_id, stop_fn=stop_fn)
+        return torch.cat([input_ids.view(1, -1).cpu(), torch.tensor([new], dtype=torch.int64)], dim=1).to(input_ids.device)
+
+    @torch.inference_mode()
+    def __call__(self, input_ids=None, use_cache=True, images=None, object_features=None, images_long=None, objects_long=None,
+                 attention_mask=None, past_key_values=None, **_):
+        e = self.engine
+        if past_key_values is None:
+            x = e.build_embeds(input_ids.view(-1).tolist(), self._px(images), self._px(object_features), images_long, objects_long)
+            T = x.shape[0]
+            e.prefill_embeds(x)
+            _, _, logits = e._logits_rows(x, torch.arange(T, dtype=torch.int64, device=e.dev))
+            return _ModelOutput(logits.view(1, T, -1), _Past(T, e.kv_epoch))
+        if past_key_values.epoch != e.kv_epoch:
+            raise RuntimeError("stale past_key_values: the engine's KV cache has been re-prefilled since this handle was returned")
+        toks = input_ids.view(-1).tolist()
+        logits = e.append_tokens(toks, past_key_values.length)          # rows of an earlier continuation are overwritten
+        return _ModelOutput(logits.view(1, len(toks), -1), _Past(past_key_values.length + len(toks), e.kv_epoch))
+
+
+def load_pretrained_model(model_path, model_base=None, model_name=None, load_8bit=False, load_4bit=False, device_map="auto",
+                          device="cuda"):
+    """Drop-in for /root/reference/LLaVA/llava/model/builder.py:26-151 (the SEAL VQA LLM branch):
+    -> (tokenizer, model, image_processor, context_len).  model_path: local `seal_vqa_7b` checkpoint directory (HF
+    safetensors / .bin shards in the reference's key layout).  bitsandbytes paths are out of scope."""
+    import os
+    if load_8bit or load_4bit:
+        raise NotImplementedError("load_8bit / load_4bit (bitsandbytes) are outside the hot-path scope (SURVEY.md §2)")
+    if not os.path.isdir(str(model_path)):
+        raise FileNotFoundError("load_pretrained_model: model_path must be a local checkpoint directory (no network here)")
+    from transformers import AutoTokenizer
+    from .vsm import config_from_hf, open_checkpoint
+    tokenizer = AutoTokenizer.from_pretrained(model_path, use_fast=False)
+    cfg = config_from_hf(model_path)
+    engine = VQAEngine(VQAWeights(cfg, open_checkpoint(model_path), device=device))
+    return tokenizer, LlavaSearchModel(engine, getattr(tokenizer, "eos_token_id", 2)), _Proc(), 2048
+
+
 class VQA_LLM:
     """Same surface as /root/reference/vstar_bench_eval.py:38-165."""
 
     def __init__(self, args=None, engine: VQAEngine = None, tokenizer=None, conv_type="v1"):
         if engine is None:
-            import os
-            from .vsm import config_from_hf, open_checkpoint
-            path = args.vqa_model_path
-            if not os.path.isdir(str(path)):
-                raise FileNotFoundError("VQA_LLM(args): args.vqa_model_path must be a local checkpoint directory")
-            from transformers import AutoTokenizer
-            tokenizer = AutoTokenizer.from_pretrained(path, use_fast=False)
-            cfg = config_from_hf(path)
-            main = open_checkpoint(path)
-            engine = VQAEngine(VQAWeights(cfg, main))
-            conv_type = getattr(args, "conv_type", "v1")
-        self.engine = self.model = engine
+            self.tokenizer, self.model, self.image_processor, self.context_len = load_pretrained_model(args.vqa_model_path, None, None)
+            self.engine = self.model.engine
+            self.conv_type = getattr(args, "conv_type", "v1")
+            self.eos = getattr(self.tokenizer, "eos_token_id", 2)
+            return
+        self.engine = engine
+        self.model = LlavaSearchModel(engine)
         self.tokenizer = tokenizer if tokenizer is not None else SyntheticTokenizer(engine.cfg)
         self.image_processor = _Proc()
         self.context_len = 2048
