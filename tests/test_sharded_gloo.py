@@ -79,3 +79,37 @@ def test_sharded_frontier_world2_gloo():
         total = n_ref
     # the two ranks split the evaluations between them (speculative batches make the split uneven but complete)
     assert sum(locals_) >= total and max(locals_) < total
+
+
+def _bcast_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vstar_b200 import synth
+    from vstar_b200.config import tiny_config
+    from vstar_b200.sharded import broadcast_loader
+    cfg = tiny_config()
+    shapes = synth.state_dict_shapes(cfg)
+    names = sorted(shapes)[:40]
+    # only rank 0 "has the checkpoint"; rank 1 passes no loader at all
+    get = (lambda n: synth.synthetic_tensor(n, shapes[n], seed=77)) if rank == 0 else None
+    load = broadcast_loader(get, src=0, device="cpu")
+    got = {n: load(n) for n in names}
+    ok = all(torch.equal(got[n], synth.synthetic_tensor(n, shapes[n], seed=77)) for n in names)
+    q.put((rank, ok, len(got)))
+    dist.destroy_process_group()
+
+
+def test_weight_broadcast_world2_gloo():
+    """start-up weight broadcast: rank 0 reads, every rank ends up with identical replicas"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30500 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_bcast_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in res) == [0, 1] and all(r[1] and r[2] == 40 for r in res)

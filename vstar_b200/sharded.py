@@ -80,3 +80,28 @@ class ShardedVSM:
         for i in range(n):
             out.append(self._unpack(parts[i % w][i // w], P, side))
         return out
+
+
+def broadcast_loader(get, src=0, group=None, device="cuda"):
+    """Weight broadcast at start-up: only rank `src` reads the checkpoint; every rank builds its replica
+    through the returned `name -> tensor` callable, which on `src` loads the tensor and broadcasts it (NCCL over NVLink on
+    the GPUs, gloo on CPU) and elsewhere receives it.  All ranks must request the same names in the same order - which they
+    do, because `CoreWeights` / `VSMWeights` / `VQAWeights` walk the reference's key layout deterministically.
+    `get` may be None on the other ranks."""
+    rank = dist.get_rank(group)
+
+    def load(name):
+        if rank == src:
+            t = get(name).to(device)
+            meta = [(tuple(t.shape), t.dtype)]
+        else:
+            t, meta = None, [None]
+        dist.broadcast_object_list(meta, src=src, group=group)
+        shape, dtype = meta[0]
+        if rank != src:
+            t = torch.empty(shape, dtype=dtype, device=device)
+        t = t.contiguous()
+        dist.broadcast(t, src=src, group=group)
+        return t
+
+    return load
