@@ -329,6 +329,22 @@ def run_b200(args):
     launches = _lib.launches - launches0
     gemm_flops, gemm_ms, gemm_n = ops.profile_end()
     clocks = sampler.stop() if rank == 0 else None
+    prefix_rows = engine._P
+
+    # transparency leg (all ranks: timed_steps synchronises them): the same resident workload with the shared-prefix KV and
+    # the tail-only last layer switched OFF, i.e. all 320 rows of every crop through all 32 layers (5.00 TFLOP/crop)
+    value_full = None
+    if not args.no_prefix_cache:
+        saved = (engine.prefix_cache, engine.tail_only)
+        try:
+            engine.prefix_cache, engine.tail_only = False, False
+            step(True)
+            ms_full, crops_full = timed_steps(min(2, args.steps), True)
+            value_full = crops_full / (ms_full / 1e3)
+        except Exception:
+            value_full = None
+        finally:
+            engine.prefix_cache, engine.tail_only = saved
 
     if rank != 0:
         if world > 1:
@@ -337,9 +353,9 @@ def run_b200(args):
 
     peak_tf, peak_hbm, peak_src = peaks()
     # executed FLOPs per crop: BASELINE.md §3's 5.00e12 minus the 7B linear work of the prefix rows that are not recomputed
-    flops_per_crop = FLOPS_PER_CROP - 2.0 * engine._P * 6.476e9
+    flops_per_crop = FLOPS_PER_CROP - 2.0 * prefix_rows * 6.476e9
     if engine.tail_only and not args.tiny:      # last layer: o-proj + MLP only on the 5 consumed rows of each crop
-        flops_per_crop -= 2.0 * (320 - engine._P - 5) * (cfg.hidden * cfg.hidden + 3 * cfg.hidden * cfg.intermediate)
+        flops_per_crop -= 2.0 * (320 - prefix_rows - 5) * (cfg.hidden * cfg.hidden + 3 * cfg.hidden * cfg.intermediate)
     value = dev_crops / (dev_ms / 1e3)
     e2e = e2e_crops / (e2e_ms / 1e3)
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
@@ -359,7 +375,8 @@ def run_b200(args):
                      "whole_path_note": ("crops/s/GPU x %.2f TFLOP/crop executed / peak (BASELINE.md §3 counts 5.00 TFLOP/crop at T=320; "
                                          "%d constant prefix rows per crop are served from the shared-prefix KV snapshot, and the last "
                                          "decoder layer runs o-proj/MLP on the 5 consumed rows only)"
-                                         % (flops_per_crop / 1e12, engine._P))},
+                                         % (flops_per_crop / 1e12, prefix_rows))},
+        "value_all_rows_all_layers": value_full,      # same leg with prefix sharing and the tail-only last layer off (5.00 TFLOP/crop)
         "crops_per_step": dev_crops // args.steps, "load_s": load_s,
         "draft_verify": engine.stats,
     }
