@@ -36,3 +36,40 @@ def test_ops_refuse_cpu_tensors_without_fallback():
         ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
     with pytest.raises(VsbError):
         ops.layernorm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.ones(8, dtype=torch.bfloat16), torch.zeros(8, dtype=torch.bfloat16), 1e-5)
+
+
+def test_ctypes_table_matches_the_header_prototypes():
+    """argument count and kind (pointer / integer / float) of every prototype in include/vstar_b200.h against the ctypes
+    argtypes the Python host uses - a mismatch would corrupt the call silently"""
+    from vstar_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "vstar_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = dict(re.findall(r"\bint\s+(vsb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S))
+    assert set(_lib.SIGNATURES) <= set(protos), sorted(set(_lib.SIGNATURES) - set(protos))
+
+    def kind_c(param):
+        param = " ".join(param.split())
+        if param in ("void", ""):
+            return None
+        if "*" in param:
+            return "p"
+        if param.startswith("float") or param.startswith("double"):
+            return "f"
+        assert re.match(r"(const )?(int|long long)\b", param), param
+        return "i"
+
+    def kind_py(t):
+        if t in (ctypes.c_float, ctypes.c_double):
+            return "f"
+        if t in (ctypes.c_int, ctypes.c_longlong):
+            return "i"
+        return "p"                                  # c_void_p, POINTER(...)
+
+    for name, argtypes in _lib.SIGNATURES.items():
+        want = [k for k in (kind_c(p) for p in protos[name].split(",")) if k is not None]
+        got = [kind_py(t) for t in argtypes]
+        assert got == want, (name, got, want)
+        # widths of the integer arguments as well
+        c_ints = [("long long" in " ".join(p.split())) for p in protos[name].split(",") if kind_c(p) == "i"]
+        py_ints = [t is ctypes.c_longlong for t in argtypes if kind_py(t) == "i"]
+        assert c_ints == py_ints, (name, c_ints, py_ints)
