@@ -122,10 +122,13 @@ int vsb_attn_small_bf16(const void* q, long long ldq, const void* k, long long l
                         int B, int H, int Nq, int Nk, int D, float scale, void* stream);
 
 /* OWL-ViT class head epilogue on y = [dense0(x) | logit_shift(x) | logit_scale(x)] (fp32) and box head epilogue
- * (modeling_owlvit.py:1043-1062; owlvit.py:63-100). */
-int vsb_owl_class_post(const void* y, long long ldy, const void* query, long long ldq, int rows_per_crop, long long R, int Q, void* logits,
-                       void* scores, void* stream);
-int vsb_owl_box_post(const void* y, long long ldy, const void* box_bias, int rows_per_crop, long long R, void* boxes, void* stream);
+ * (modeling_owlvit.py:1043-1062; owlvit.py:63-100).  quant_bf16 != 0: logits / sigmoid scores / boxes are rounded to bf16
+ * VALUES (kept in fp32 storage), which is what the reference's bf16 model hands to the search loop (visual_search.py:145,
+ * :223-224, :399-409): thresholds, argmax ties and all_valid_boxes are then decided on the same numbers. */
+int vsb_owl_class_post(const void* y, long long ldy, const void* query, long long ldq, int rows_per_crop, long long R, int Q, int quant_bf16,
+                       void* logits, void* scores, void* stream);
+int vsb_owl_box_post(const void* y, long long ldy, const void* box_bias, int rows_per_crop, long long R, int quant_bf16, void* boxes,
+                     void* stream);
 
 /* SAM mask-decoder upscaling helpers (mask_decoder.py:15-27, :78-84, :169-181), channels-last. */
 int vsb_upsample2x_nhwc_bf16(const void* x, void* y, int B, int H, int W, int C, void* stream);
@@ -138,6 +141,22 @@ int vsb_heatmap_bilinear_f32(const void* low, int LH, int LW, void* out, int h, 
 /* sums of the min-max-normalised heatmap over integer rectangles [x,y,w,h] (visual_search.py:255-266). */
 int vsb_rect_sums_f32(const void* hm, int h, int w, const void* rects_i32, int nrects, const void* stats3, void* out_f64,
                       void* scratch_f64 /* 64*nrects doubles */, void* stream);
+
+/* Crop records: everything the search controller consumes from one crop evaluation as a fixed-size
+ * fp32 record rec[row*R ..]: [0] best sigmoid score, [1..4] its cxcywh box, [5] rows P, [6] rows with score > 0.5, [7] best row
+ * (-1 = no finite score), [8..10] (max,min,sum) of the clamped target-cue map, [11] number of rectangle sums, [12..75] first 16
+ * boxes with score > 0.5 in row order, [76..] rectangle sums.
+ * vsb_pack_detections_f32 fills [0..7] and [12..75] for n_crops consecutive records from scores [n,P] / boxes [n,P,4]
+ * (argmax with first-index tie-break = torch.argmax; visual_search.py:399-409).
+ * vsb_heat_pyramids_f32 fills [8..11] and [76..] for n_jobs crops WITHOUT writing the H x W map: statistics and the sums of the
+ * min-max-normalised map over integer rectangles (the crop itself and its quad-tree descendants: get_subpatch_scores over the
+ * ancestor chain, visual_search.py:255-275, :453-462) are evaluated from the LH x LW low-res mask with the arithmetic of
+ * vsb_heatmap_bilinear_f32 + vsb_rect_sums_f32 (bit-identical).  jobs_i32: 8 ints per job {low_ptr lo, low_ptr hi, h, w, first
+ * rect, n_rects, record row, 0}; rects_i32 [total,4] = x,y,w,h relative to the crop; rect_job_i32 [total] = owning job;
+ * scratch: 192*n_jobs floats, 64*total_rects doubles. */
+int vsb_pack_detections_f32(const void* scores, const void* boxes, int n_crops, int P, void* rec, long long R, void* stream);
+int vsb_heat_pyramids_f32(const void* jobs_i32, int n_jobs, const void* rects_i32, const void* rect_job_i32, int total_rects, int LH,
+                          int LW, void* rec, long long R, void* scratch_stats_f32, void* scratch_rects_f64, void* stream);
 
 /* Pillow-exact antialiased BICUBIC resize of a uint8 RGB crop resident on the device, in Pillow's two integer passes
  * (libImaging/Resample.c 8bpc path; coefficient tables from vstar_b200/image.py), fused with /255, CLIP mean/std and the

@@ -178,34 +178,7 @@ def case_generate(m, sd, cfg, tag, img_seed, w, h, n_text):
 
 
 # ---------------------------------------------------------------- search goldens
-class StubVSM:
-    """Deterministic stand-in for visual_search.VSM: outputs depend only on the
-    crop's pixels (so they are pure functions of the crop, like the real VSM)."""
-
-    def __init__(self, hot=None):
-        self.calls = []
-        self.hot = hot
-
-    def inference(self, image, question, mode="segmentation"):
-        arr = np.asarray(image, dtype=np.uint8)
-        h, w = arr.shape[:2]
-        self.calls.append((w, h, mode))
-        s = int(arr[::max(1, h // 16), ::max(1, w // 16)].astype(np.int64).sum()) % (2 ** 31)
-        rng = np.random.default_rng(s)
-        if mode == "vqa":
-            return "The object is most likely to appear near the table."
-        low = rng.standard_normal((12, 12)).astype(np.float32) * 4.0
-        hm = torch.nn.functional.interpolate(torch.from_numpy(low)[None, None], (h, w), mode="bilinear",
-                                             align_corners=False)[0, 0].clamp(min=0)
-        if mode == "segmentation":
-            return hm
-        logits = torch.from_numpy(rng.uniform(0.0, 0.45, (2304, 1)).astype(np.float32))
-        boxes = torch.from_numpy(rng.uniform(0.1, 0.9, (2304, 4)).astype(np.float32))
-        if self.hot == "root" and min(w, h) >= 600:
-            logits[100, 0], logits[7, 0], logits[2000, 0] = 0.9, 0.7, 0.6
-        if self.hot == "small" and min(w, h) <= 300:
-            logits[55, 0] = 0.8
-        return boxes, logits, hm
+from tests.helpers import FakeNLP, StubVSM  # noqa: E402  (deterministic stub VSM + rule parser standing in for spaCy)
 
 
 def trajectory(search_path):
@@ -215,23 +188,29 @@ def trajectory(search_path):
 def case_search(tag, img_seed, w, h, smallest, hot=None, **kw):
     print(f"[golden] search case {tag}")
     import visual_search as RVS  # the reference module
+    from vstar_b200.noun_chunks import extract_noun_chunks
+    nlp = FakeNLP()
+    RVS.nlp = nlp                # the reference's module-level spaCy pipeline (visual_search.py:10) -> deterministic rule parser
     img = synth_image(img_seed, w, h)
     stub = StubVSM(hot)
     fs, pl, ok, av = RVS.visual_search(stub, img, "mug", None, smallest, **kw)
     ref_calls = list(stub.calls)
     stub2 = StubVSM(hot)
-    fs2, pl2, ok2, av2, path2 = O.visual_search(stub2, img, "mug", None, smallest, **kw)
+    fs2, pl2, ok2, av2, path2 = O.visual_search(stub2, img, "mug", None, smallest,
+                                                extract_noun_chunks=lambda t: extract_noun_chunks(t, nlp), **kw)
     assert ref_calls == stub2.calls
     assert pl == pl2 and ok == ok2 and fs["bbox"] == fs2["bbox"]
     assert torch.equal(fs["detection_result"], fs2["detection_result"])
     assert (av is None) == (av2 is None) and (av is None or torch.equal(av, av2))
+    cues = [st.get("context_cue", "") for st in path2]
     np.savez_compressed(os.path.join(GOLDEN_DIR, f"search_{tag}.npz"), img_seed=img_seed, w=w, h=h, smallest=smallest,
                         kw=json.dumps(kw), hot=str(hot), all_valid_boxes=(av.numpy() if av is not None else np.zeros((0, 4), np.float32)),
-                        has_all_valid=int(av is not None), calls=np.array([(c[0], c[1], {"detection": 0, "vqa": 1, "segmentation": 2}[c[2]])
-                                                           for c in ref_calls], dtype=np.int64),
+                        has_all_valid=int(av is not None), calls=np.array(ref_calls, dtype=np.int64).reshape(-1, 3),
                         trajectory=trajectory(path2), path_length=pl, success=int(ok), final_bbox=np.array(fs["bbox"]),
-                        detection_result=fs["detection_result"].numpy())
-    print(f"   {len(ref_calls)} VSM calls, path_length={pl}, success={ok}")
+                        detection_result=fs["detection_result"].numpy(), context_cues=json.dumps(cues))
+    n_one = sum(1 for c in cues if c and not c.split("#")[-1].startswith("region "))
+    print(f"   {len(ref_calls)} VSM calls, path_length={pl}, success={ok}, weak-cue nodes={sum(1 for c in cues if c)} "
+          f"(single-chunk phrases: {n_one})")
 
 
 class RefModelVSM:
@@ -421,8 +400,17 @@ def main():
     case_search("stub_default", img_seed=22, w=1500, h=700, smallest=224)
     case_search("stub_weakcue", img_seed=23, w=900, h=1900, smallest=300, confidence_high=2.0,
                 target_cue_threshold=50.0, target_cue_threshold_minimum=40.0)
+    # strong and weak cues mixed (threshold inside the stub's score range): both branches of visual_search.py:422-443, and
+    # phrases with zero / one / several noun chunks
+    case_search("stub_mixcue", img_seed=29, w=1600, h=1200, smallest=224, confidence_high=2.0,
+                target_cue_threshold=9.5, target_cue_threshold_minimum=9.5)
     search_edge_cases()
     case_search_model(m, sd, cfg, "a", img_seed=31, w=640, h=512, smallest=200, confidence_high=2.0,
+                      target_cue_threshold=-1e9, target_cue_threshold_minimum=-1e9)
+    # more reference-model x reference-search trajectories: another seed, and a tall image whose root splits 1x4
+    case_search_model(m, sd, cfg, "b", img_seed=32, w=600, h=600, smallest=160, confidence_high=2.0,
+                      target_cue_threshold=-1e9, target_cue_threshold_minimum=-1e9)
+    case_search_model(m, sd, cfg, "c", img_seed=33, w=300, h=960, smallest=200, confidence_high=2.0,
                       target_cue_threshold=-1e9, target_cue_threshold_minimum=-1e9)
     case_vqa("a", img_seed=41)
     case_bench_eval()

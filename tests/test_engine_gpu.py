@@ -157,13 +157,58 @@ def test_shared_prefix_kv_equals_full_prefill(setup):
     shared = {k: v.clone() for k, v in eng.model_forward(io, ic, idb).items() if k in keys}                # 4 crops, 2 new slots
     img_pos = int((ids[0] == -200).nonzero()[0, 0])
     assert eng._P == img_pos - 1 and eng.stats["prefix_shared"] == n0 + 4
-    for k in keys:
-        assert err(first[k], full[k][:2]) < 1e-6, k
-        assert err(shared[k], full[k]) < 2e-3, (k, err(shared[k], full[k]))
     REPORT["shared_prefix_err"] = {k: err(shared[k], full[k]) for k in keys}
+    for k in keys:
+        assert torch.equal(first[k], full[k][:2]), k
+        # the rows from <im_start> on see bit-identical inputs (same K/V rows, same kernels): EXACT equality, as DESIGN.md states
+        assert torch.equal(shared[k], full[k]), (k, err(shared[k], full[k]))
     # draft-verify path on top of the shared prefix
     out = eng.inference(io, ic, prompt.expand(4, -1).contiguous(), ans.tolist(), forced_ids=ans.tolist())
     assert err(out["low_res_masks"], full["low_res_masks"]) < 2e-3 and eng._P == img_pos - 1
+
+
+def test_prefix_bookkeeping_survives_a_different_prefix_batch(setup):
+    """a full (P = 0) prefill with ANOTHER prefix overwrites cache rows 0..T of its slots; a later shared-prefix
+    prefill must re-copy the snapshot instead of trusting the stale slots"""
+    O, cfg, sd, sd_bf, eng = setup
+    prompt, ans = O.synthetic_prompt(cfg, n_text=40, seed=8)
+    ids = torch.cat([prompt, ans.unsqueeze(0)], 1)
+    other = ids.clone()
+    other[0, 3] = (int(other[0, 3]) + 7) % 200 + 3            # one different token inside the prefix
+    imgs = [synth_image(300 + i, 100 + 10 * i, 90 + 9 * i) for i in range(3)]
+    ic = torch.cat([O.preprocess_clip(i) for i in imgs]).to(BF).cuda()
+    io = torch.cat([O.preprocess_owl(i) for i in imgs]).to(BF).cuda()
+    idb = ids.expand(3, -1).contiguous().cuda()
+    keys = ("hidden_loc", "low_res_masks", "pred_logits")
+    eng._prefix_ids = None
+    want = {k: v.clone() for k, v in eng.model_forward(io, ic, idb).items() if k in keys}          # computes + snapshots
+    again = {k: v.clone() for k, v in eng.model_forward(io, ic, idb).items() if k in keys}        # shared prefix
+    assert eng._P > 0
+    mixed = torch.cat([ids, other], 0).cuda()                 # non-uniform heads: full prefill, snapshot kept
+    eng.model_forward(io[:2], ic[:2], mixed)
+    assert eng._P == 0 and eng._prefix_slots == 0
+    after = {k: v.clone() for k, v in eng.model_forward(io, ic, idb).items() if k in keys}        # must re-copy the prefix rows
+    assert eng._P > 0
+    for k in keys:
+        assert torch.equal(again[k], after[k]), k
+        assert err(after[k], want[k]) < 2e-3
+
+
+def test_cache_grows_instead_of_truncating(setup):
+    """generation beyond the initial cache rows grows the cache (up to the 2048 RoPE rows); nothing stops silently"""
+    O, cfg, sd, sd_bf, eng = setup
+    prompt, ans = O.synthetic_prompt(cfg, n_text=24, seed=3)
+    img = synth_image(7, 100, 100)
+    ic = O.preprocess_clip(img).to(BF).cuda()
+    old = eng.max_tokens
+    eng.max_tokens, eng._cache, eng._cache_shape = 64, None, None
+    try:
+        out, am = eng.generate(prompt, ic, max_new_tokens=40, eos_token_id=-1)
+        assert len(am) == 40 and eng._cache_shape[2] >= prompt.shape[1] + 255 + 40 - 1
+        with pytest.raises(Exception):
+            eng._capacity(4096)
+    finally:
+        eng.max_tokens, eng._cache, eng._cache_shape = old, None, None
 
 
 def test_zz_write_report(setup):

@@ -108,6 +108,15 @@ def check_prompts_and_token_splicing():
         conv.append_message(conv.roles[0], prompt)
         conv.append_message(conv.roles[1], "")
         assert vsm.build_prompt(q, "llava_v1", True) == conv.get_prompt()
+        for use_se in (True, False):                 # the other template the CLI accepts (visual_search.py:48)
+            c2 = rc_vsm.conv_templates["llava_llama_2"].copy()
+            c2.messages = []
+            p2 = "<image>" + "\n" + q
+            if use_se:
+                p2 = p2.replace("<image>", "<im_start><image><im_end>")
+            c2.append_message(c2.roles[0], p2)
+            c2.append_message(c2.roles[1], "")
+            assert vsm.build_prompt(q, "llava_llama_2", use_se) == c2.get_prompt()
         ours = vsm.tokenizer_image_token(conv.get_prompt(), tok)
         theirs = ref_tok(conv.get_prompt(), tok, return_tensors="pt").tolist()
         assert ours == theirs and ours.count(-200) == 1
@@ -147,7 +156,36 @@ def check_padding_and_patch_geometry():
             assert get_patch(None, bbox, W, H, patch_scale=scale) == get_patch_ref(None, bbox, W, H, patch_scale=scale)
 
 
-@pytest.mark.parametrize("name", ["check_split_and_sub_patches", "check_refine_bbox_and_iou", "check_prioritize_pop_order_with_ties",
+def check_noun_chunks():
+    """extract_noun_chunks / get_noun_chunks / filter_chunk_list (visual_search.py:54-112) with the SAME deterministic parser
+    on both sides (spaCy is not installed offline): random phrases from the rule parser's lexicon + hand-made trees"""
+    ref = load_reference()
+    from tests.helpers import FakeNLP, VQA_ANSWERS
+    from vstar_b200 import noun_chunks as NC
+    nlp = FakeNLP()
+    ref.nlp = nlp
+    rng = np.random.default_rng(7)
+    words = sorted(FakeNLP.NOUNS | FakeNLP.PRONS | FakeNLP.ADJS | FakeNLP.DETS | FakeNLP.PREPS | FakeNLP.RELS) + ["and", "somewhere", "high", "is"]
+    phrases = [a.split("most likely to appear")[-1].strip().rstrip(".") for a in VQA_ANSWERS]
+    for _ in range(3000):
+        phrases.append(" ".join(rng.choice(words, size=int(rng.integers(1, 12)))))
+    n_multi = n_one = n_zero = 0
+    for ph in phrases:
+        got, want = NC.extract_noun_chunks(ph, nlp), ref.extract_noun_chunks(ph)
+        assert got == want, (ph, got, want)
+        n_multi += len(got) > 1
+        n_one += len(got) == 1
+        n_zero += len(got) == 0
+        doc = nlp(ph)
+        for t in doc:
+            assert NC.get_noun_chunks(t) == ref.get_noun_chunks(t) and NC.subtree_span(t) == ref.tranverse(t)
+    assert n_multi > 100 and n_one > 100 and n_zero > 10
+    for _ in range(2000):
+        chunks = [tuple(sorted(rng.integers(0, 30, 2).tolist())) for _ in range(int(rng.integers(0, 8)))]
+        assert NC.filter_chunk_list(chunks) == ref.filter_chunk_list(chunks)
+
+
+@pytest.mark.parametrize("name", ["check_noun_chunks", "check_split_and_sub_patches", "check_refine_bbox_and_iou", "check_prioritize_pop_order_with_ties",
                                   "check_prompts_and_token_splicing", "check_padding_and_patch_geometry"])
 def test_against_live_reference(name):
     isolated(name)

@@ -448,6 +448,79 @@ def test_heatmap_and_rect_sums(ops, h, w):
         assert abs(float(sums[i]) - want) <= 1e-5 * abs(want) + 1e-4, (i, float(sums[i]), want)
 
 
+@pytest.mark.parametrize("h,w,smallest", [(110, 150, 40), (512, 512, 100), (1900, 900, 300), (777, 1001, 251), (1024, 1024, 224)])
+def test_crop_records_equal_materialised_path(ops, h, w, smallest):
+    """vsb_pack_detections_f32 + vsb_heat_pyramids_f32 (no H x W map written) == heatmap + rect_sums + torch reductions,
+    bit for bit: statistics, every rectangle sum of the quad-tree pyramid (cast to fp32 as the controller does), best
+    score/box with first-index tie-break, count and compaction of the boxes above 0.5"""
+    import numpy as np
+    from vstar_b200 import records as RC
+    g = torch.Generator(device="cuda").manual_seed(h * 7 + w)
+    n, P = 3, 2304
+    lows = torch.randn(n, 192, 192, device="cuda", generator=g) * 3
+    scores = torch.rand(n, P, device="cuda", generator=g) * 0.45
+    scores[0, 100], scores[0, 7], scores[0, 2000] = 0.9, 0.9, 0.6          # tie for the maximum: first index (7) must win
+    scores[1, 40:70] = torch.linspace(0.95, 0.55, 30, device="cuda")        # 30 valid rows: only the first 16 are recorded
+    boxes = torch.rand(n, P, 4, device="cuda", generator=g)
+    bboxes = [[13, 29, w, h], [0, 0, w, h], [5, 0, w, h]]
+    rects = [RC.pyramid_rects(b, smallest) for b in bboxes]
+    rects[2] = []                                                          # a crop that is never split: no heat-map part
+    R = RC.record_floats(max(len(r) for r in rects))
+    rec = torch.zeros(n, R, device="cuda")
+    ops.pack_detections(scores, boxes, rec)
+    jobs = [(lows[i], h, w, [(r[0] - bboxes[i][0], r[1] - bboxes[i][1], r[2], r[3]) for r in rects[i]], i) for i in range(n) if rects[i]]
+    ops.heat_pyramids(jobs, rec, 192, 192)
+    rows = rec.cpu().numpy()
+    for i in range(n):
+        ti = int(scores[i].argmax())
+        assert rows[i, RC.REC_TOPIDX] == ti and rows[i, RC.REC_TOP] == float(scores[i, ti]) and rows[i, RC.REC_NROWS] == P
+        assert np.array_equal(rows[i, RC.REC_BOX:RC.REC_BOX + 4], boxes[i, ti].cpu().numpy())
+        valid = (scores[i] > 0.5).nonzero().flatten()
+        assert rows[i, RC.REC_NVALID] == len(valid)
+        k = min(len(valid), RC.REC_MAXVALID)
+        assert np.array_equal(rows[i, RC.REC_VALID:RC.REC_VALID + 4 * k].reshape(k, 4), boxes[i, valid[:k]].cpu().numpy())
+        if not rects[i]:
+            assert rows[i, RC.REC_NRECT] == 0
+            continue
+        hm, stats = ops.heatmap(lows[i].contiguous(), h, w)
+        s = stats.cpu().numpy()
+        assert rows[i, RC.REC_MAX] == s[0] == float(hm.max()) and rows[i, RC.REC_MIN] == s[1] == float(hm.min())
+        assert abs(rows[i, RC.REC_SUM] - float(hm.double().sum())) <= 1e-5 * float(hm.double().sum()) + 1e-3
+        assert rows[i, RC.REC_NRECT] == len(rects[i])
+        rel = torch.tensor(jobs[[j[4] for j in jobs].index(i)][3], dtype=torch.int32, device="cuda")
+        want = ops.rect_sums(hm, rel, stats).cpu().numpy().astype(np.float32)
+        got = rows[i, RC.REC_PYR:RC.REC_PYR + len(rects[i])]
+        assert np.array_equal(got, want), float(np.abs(got - want).max())
+        # and against numpy: normalize_score per element in fp32 (IEEE division, like torch), float64 sums
+        norm = ((hm - hm.min()) / (hm.max() - hm.min())).double().cpu().numpy()
+        for (x, y, rw, rh), v in list(zip(jobs[[j[4] for j in jobs].index(i)][3], got))[:9]:
+            assert abs(float(v) - norm[y:y + rh, x:x + rw].sum()) <= 2e-7 * norm[y:y + rh, x:x + rw].sum() + 1e-6
+        ev = __import__("vstar_b200.visual_search", fromlist=["_NodeEval"])._NodeEval.from_record(rows[i], bboxes[i], smallest)
+        assert ev.pyramid is not None and ev.pyramid.get(tuple(bboxes[i])) == float(got[0])
+    # NaN scores: no finite maximum is reported instead of an out-of-range index (ADVICE r1)
+    bad = torch.full((1, P), float("nan"), device="cuda")
+    rec1 = torch.zeros(1, R, device="cuda")
+    ops.pack_detections(bad, boxes[:1].contiguous(), rec1)
+    assert float(rec1[0, RC.REC_TOPIDX]) == -1
+
+
+def test_owl_head_epilogues_bf16_values(ops):
+    """quant_bf16: logits / scores / boxes are bf16 VALUES (the reference model is bf16, visual_search.py:145): equal to
+    rounding the fp32 results, and many rows tie at the maximum exactly as they do in the reference"""
+    y = torch.randn(2 * 2304, 66, device="cuda")
+    q = rnd(2, 64, seed=4)
+    l0, s0 = ops.owl_class_post(y, q, 2304, 64)
+    l1, s1 = ops.owl_class_post(y, q, 2304, 64, quant_bf16=True)
+    assert torch.equal(l1, l0.to(BF).float()) and torch.equal(s1, s1.to(BF).float())
+    assert float((s1 != torch.sigmoid(l1).to(BF).float()).float().mean()) < 1e-3       # expf vs torch's sigmoid: fp32 ulp at a bf16 tie
+    yb = torch.randn(2304, 4, device="cuda")
+    bias = torch.randn(2304, 4, device="cuda")
+    b0 = ops.owl_box_post(yb, bias, 2304)
+    b1 = ops.owl_box_post(yb, bias, 2304, quant_bf16=True)
+    want = torch.sigmoid((yb.to(BF).float() + bias).to(BF).float()).to(BF).float()
+    assert torch.equal(b1, b1.to(BF).float()) and float((b1 != want).float().mean()) < 1e-3 and float((b1 - b0).abs().max()) < 1.2e-2
+
+
 def test_copy2d_and_cast(ops):
     src = rnd(50, 3 * 128, seed=90)
     dst = torch.zeros(50, 2 * 128, dtype=BF, device="cuda")

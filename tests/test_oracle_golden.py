@@ -69,36 +69,20 @@ def test_generate_golden(tiny):
     assert free == list(g["free_argmax"])
 
 
-class StubVSM:
-    # identical to oracle/make_golden.py:StubVSM (pure function of crop pixels)
-    def __init__(self):
-        self.calls = []
-
-    def inference(self, image, question, mode="segmentation"):
-        arr = np.asarray(image, dtype=np.uint8)
-        h, w = arr.shape[:2]
-        self.calls.append((w, h, {"detection": 0, "vqa": 1, "segmentation": 2}[mode]))
-        s = int(arr[::max(1, h // 16), ::max(1, w // 16)].astype(np.int64).sum()) % (2 ** 31)
-        rng = np.random.default_rng(s)
-        if mode == "vqa":
-            return "The object is most likely to appear near the table."
-        low = rng.standard_normal((12, 12)).astype(np.float32) * 4.0
-        hm = torch.nn.functional.interpolate(torch.from_numpy(low)[None, None], (h, w), mode="bilinear",
-                                             align_corners=False)[0, 0].clamp(min=0)
-        if mode == "segmentation":
-            return hm
-        logits = torch.from_numpy(rng.uniform(0.0, 0.45, (2304, 1)).astype(np.float32))
-        boxes = torch.from_numpy(rng.uniform(0.1, 0.9, (2304, 4)).astype(np.float32))
-        return boxes, logits, hm
+from tests.helpers import FakeNLP, StubVSM  # noqa: E402  (the stub the goldens were generated with, oracle/make_golden.py)
 
 
-@pytest.mark.parametrize("tag", ["stub_3lvl", "stub_default", "stub_weakcue"])
+@pytest.mark.parametrize("tag", ["stub_3lvl", "stub_default", "stub_weakcue", "stub_mixcue"])
 def test_search_trajectory_golden(tag):
+    from vstar_b200.noun_chunks import extract_noun_chunks
     g = np.load(os.path.join(G, f"search_{tag}.npz"))
     img = synth_image(int(g["img_seed"]), int(g["w"]), int(g["h"]))
     kw = json.loads(str(g["kw"]))
     stub = StubVSM()
-    fs, pl, ok, av, path = O.visual_search(stub, img, "mug", None, int(g["smallest"]), **kw)
+    nlp = FakeNLP()
+    fs, pl, ok, av, path = O.visual_search(stub, img, "mug", None, int(g["smallest"]),
+                                           extract_noun_chunks=lambda t: extract_noun_chunks(t, nlp), **kw)
+    assert [s.get("context_cue", "") for s in path] == json.loads(str(g["context_cues"]))
     assert np.array_equal(np.array(stub.calls), g["calls"])
     assert np.array_equal(np.array([s["bbox"] for s in path]), g["trajectory"])
     assert pl == int(g["path_length"]) and int(ok) == int(g["success"])

@@ -9,10 +9,19 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import NumpyScorer, StubVSM, synth_image
+from tests.helpers import FakeNLP, NumpyScorer, RecordStub, StubVSM, synth_image
+from vstar_b200 import noun_chunks
 from vstar_b200 import visual_search as VS
 
 G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(autouse=True)
+def fake_nlp():
+    """the goldens were generated with the reference's spaCy pipeline replaced by tests.helpers.FakeNLP (oracle/make_golden.py)"""
+    noun_chunks.set_nlp(FakeNLP())
+    yield
+    noun_chunks.set_nlp(None)
 
 
 EDGE_TAGS = ["edge_root_hit", "edge_deep_hit", "edge_tiny", "edge_tiny_unsure", "edge_wide", "edge_odd"]
@@ -23,7 +32,23 @@ def golden_stub(g):
     return StubVSM(None if hot == "None" else hot)
 
 
-@pytest.mark.parametrize("tag", ["stub_3lvl", "stub_default", "stub_weakcue"] + EDGE_TAGS)
+ALL_TAGS = ["stub_3lvl", "stub_default", "stub_weakcue", "stub_mixcue"] + EDGE_TAGS
+
+
+def check_against_golden(g, stub, fs, pl, ok, av, st):
+    if "has_all_valid" in g.files:
+        assert (av is not None) == bool(int(g["has_all_valid"]))
+        if av is not None:
+            assert np.array_equal(av.numpy(), g["all_valid_boxes"])
+    assert np.array_equal(np.array([s["bbox"] for s in st.search_path]), g["trajectory"])
+    assert pl == int(g["path_length"]) and int(ok) == int(g["success"])
+    assert list(fs["bbox"]) == list(g["final_bbox"])
+    assert np.allclose(fs["detection_result"].numpy(), g["detection_result"], rtol=0, atol=0)
+    # the context-cue strings pin the noun-chunk logic (visual_search.py:430-442): answer + "#" + phrase per weak-cue node
+    assert [s.get("context_cue", "") for s in st.search_path] == json.loads(str(g["context_cues"]))
+
+
+@pytest.mark.parametrize("tag", ALL_TAGS)
 def test_trajectory_matches_reference(tag):
     """trajectories, VSM call sequences and return values of the REAL reference visual_search(); the edge_* cases cover its
     termination / selection branches: confident hit at the root with several valid boxes (visual_search.py:404-410), hit
@@ -34,15 +59,75 @@ def test_trajectory_matches_reference(tag):
     kw = json.loads(str(g["kw"]))
     stub = golden_stub(g)
     fs, pl, ok, av, st = VS.visual_search(stub, img, "mug", None, int(g["smallest"]), scorer=NumpyScorer(), return_state=True, **kw)
-    if "has_all_valid" in g.files:
-        assert (av is not None) == bool(int(g["has_all_valid"]))
-        if av is not None:
-            assert np.array_equal(av.numpy(), g["all_valid_boxes"])
-    assert np.array_equal(np.array([s["bbox"] for s in st.search_path]), g["trajectory"])
+    check_against_golden(g, stub, fs, pl, ok, av, st)
     assert np.array_equal(np.array(stub.calls), g["calls"])
-    assert pl == int(g["path_length"]) and int(ok) == int(g["success"])
-    assert list(fs["bbox"]) == list(g["final_bbox"])
-    assert np.allclose(fs["detection_result"].numpy(), g["detection_result"], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("batch", [1, 4, 32])
+@pytest.mark.parametrize("tag", ALL_TAGS)
+def test_record_path_pipelined_matches_reference(tag, batch):
+    """the product path: crop RECORDS (rectangle-sum pyramids instead of heat maps) + pipelined launch/finish controller with
+    speculative batches must still walk the reference's trajectory and return its results"""
+    g = np.load(os.path.join(G, f"search_{tag}.npz"))
+    img = synth_image(int(g["img_seed"]), int(g["w"]), int(g["h"]))
+    kw = json.loads(str(g["kw"]))
+    hot = str(g["hot"]) if "hot" in g.files else "None"
+    stub = RecordStub(None if hot == "None" else hot)
+    fs, pl, ok, av, st = VS.visual_search(stub, img, "mug", None, int(g["smallest"]), scorer=NumpyScorer(), batch_size=batch,
+                                          return_state=True, **kw)
+    check_against_golden(g, stub, fs, pl, ok, av, st)
+    assert max(stub.batches) <= batch
+    # the lazily materialised final_heatmap of an expanded node is the reference's [h,w,1] fp32 normalised map
+    node = st.search_path[0]
+    if "final_heatmap" in node and tag == "stub_3lvl":
+        a = np.asarray(node["final_heatmap"])
+        assert a.shape == (int(g["h"]), int(g["w"]), 1) and float(a.max()) == 1.0 and float(a.min()) == 0.0
+
+
+def test_more_than_16_valid_boxes_at_the_root():
+    """all_valid_boxes when the record's 16 slots overflow: fetched from the owner, equal to the map-based path"""
+    img = synth_image(24, 1280, 960)
+    a = VS.visual_search(StubVSM("many"), img, "mug", None, 224, scorer=NumpyScorer())
+    b = VS.visual_search(RecordStub("many"), img, "mug", None, 224, scorer=NumpyScorer(), batch_size=4)
+    assert a[3] is not None and a[3].shape == (30, 4) and torch.equal(a[3], b[3])
+    assert a[1] == b[1] and a[2] == b[2] and torch.equal(a[0]["detection_result"], b[0]["detection_result"])
+
+
+def test_missing_spacy_raises_instead_of_degrading():
+    """the weak-cue branch must not silently fall back to 'region {phrase}' when spaCy is absent"""
+    noun_chunks.set_nlp(None)
+    try:
+        import spacy  # noqa: F401
+        pytest.skip("spaCy is installed here")
+    except ImportError:
+        pass
+    g = np.load(os.path.join(G, "search_stub_weakcue.npz"))
+    img = synth_image(int(g["img_seed"]), int(g["w"]), int(g["h"]))
+    with pytest.raises(noun_chunks.NounChunkerUnavailable):
+        VS.visual_search(StubVSM(), img, "mug", None, int(g["smallest"]), scorer=NumpyScorer(), **json.loads(str(g["kw"])))
+
+
+def test_pyramid_rects_geometry():
+    """record pyramid = the node, then the children of every expandable descendant, in BFS order; leaves tile the node"""
+    from vstar_b200 import records as RC
+    for bbox, ss in (([0, 0, 1024, 1024], 224), ([10, 20, 1001, 777], 251), ([0, 0, 2000, 420], 224), ([5, 5, 300, 1900], 300),
+                     ([0, 0, 200, 150], 224)):
+        rects = RC.pyramid_rects(bbox, ss)
+        if not RC.expandable(bbox, ss):
+            assert rects == []
+            continue
+        assert rects[0] == tuple(bbox)
+        want, level = [tuple(bbox)], [bbox]
+        while level:
+            nxt = []
+            for b in level:
+                subs, _, _ = VS.get_sub_patches(b, *VS.split_4subpatches(b))
+                assert sum(s[2] * s[3] for s in subs) == b[2] * b[3]          # children tile the parent exactly
+                want += [tuple(s) for s in subs]
+                nxt += [s for s in subs if min(s[2], s[3]) > ss]
+            level = nxt
+        assert rects == want and len(set(rects)) == len(rects)
+        assert RC.record_floats(len(rects)) % 4 == 0 and RC.record_floats(len(rects)) >= 76 + len(rects)
 
 
 class BatchStub(StubVSM):
@@ -55,8 +140,8 @@ class BatchStub(StubVSM):
     def detect_batch(self, images, questions):
         self.batches.append(len(images))
         out = []
-        for im in images:
-            boxes, logits, hm = StubVSM.inference(self, im, "", "detection")
+        for im, q in zip(images, questions):
+            boxes, logits, hm = StubVSM.inference(self, im, q, "detection")
             ev = VS._NodeEval()
             ev.n_logits = len(logits)
             ev.top_logit = logits.view(-1).max()

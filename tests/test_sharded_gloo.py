@@ -14,50 +14,39 @@ from tests.helpers import NumpyScorer, StubVSM, synth_image
 G = os.path.join(os.path.dirname(__file__), "golden")
 
 
-class RegionStub(StubVSM):
-    """pure function of the crop, through the detect_regions interface the CUDA VSM exposes (CPU tensors here)"""
-
-    def __init__(self):
-        super().__init__()
-        self.n_local = 0
-
-    def detect_regions(self, regions, questions):
-        from vstar_b200.visual_search import _NodeEval
-        out = []
-        for src, b in regions:
-            self.n_local += 1
-            im = src.crop((int(b[0]), int(b[1]), int(b[0] + b[2]), int(b[1] + b[3])))
-            boxes, logits, hm = StubVSM.inference(self, im, "", "detection")
-            ev = _NodeEval()
-            ev.n_logits = len(logits)
-            ev.top_logit = float(logits.view(-1).max())
-            ev.top_box = boxes[int(logits.view(-1).argmax())].clone()
-            ev.boxes, ev.scores = boxes, logits
-            # a 192x192 "low-res" map; the controller up-samples it like the real one
-            arr = np.asarray(im, dtype=np.uint8)
-            s = int(arr[::max(1, arr.shape[0] // 16), ::max(1, arr.shape[1] // 16)].astype(np.int64).sum()) % (2 ** 31)
-            ev.low_res = torch.from_numpy(np.random.default_rng(s).standard_normal((192, 192)).astype(np.float32) * 3)
-            out.append(ev)
-        return out
-
-
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests.helpers import FakeNLP, RecordStub
+    from vstar_b200 import noun_chunks
     from vstar_b200 import visual_search as VS
     from vstar_b200.sharded import ShardedVSM
-    img = synth_image(21, 512, 512)
-    kw = dict(confidence_high=2.0, target_cue_threshold=-1e9, target_cue_threshold_minimum=-1e9)
-    inner = RegionStub()
-    sh = ShardedVSM(inner, device="cpu")
-    fs, pl, ok, av, st = VS.visual_search(sh, img, "mug", None, 100, scorer=NumpyScorer(), batch_size=8, return_state=True, **kw)
-    traj = [tuple(s["bbox"]) for s in st.search_path]
-    # un-sharded run in the same process
-    ref = RegionStub()
-    fs2, pl2, ok2, av2, st2 = VS.visual_search(ref, img, "mug", None, 100, scorer=NumpyScorer(), batch_size=8, return_state=True, **kw)
-    q.put((rank, traj == [tuple(s["bbox"]) for s in st2.search_path], pl == pl2, inner.n_local, ref.n_local,
-           torch.equal(fs["detection_result"], fs2["detection_result"])))
+    noun_chunks.set_nlp(FakeNLP())
+    out = []
+    # (image seed, w, h, smallest, kw, hot): full-depth strong-cue search; mixed strong/weak cues; > 16 valid boxes at a successful root
+    cases = [(21, 512, 512, 100, dict(confidence_high=2.0, target_cue_threshold=-1e9, target_cue_threshold_minimum=-1e9), None),
+             (29, 800, 600, 224, dict(confidence_high=2.0, target_cue_threshold=9.5, target_cue_threshold_minimum=9.5), None),
+             (24, 1280, 960, 224, dict(), "many")]
+    for seed, w, h, smallest, kw, hot in cases:
+        img = synth_image(seed, w, h)
+        inner = RecordStub(hot)
+        sh = ShardedVSM(inner, device="cpu")
+        fs, pl, ok, av, st = VS.visual_search(sh, img, "mug", None, smallest, scorer=NumpyScorer(), batch_size=8, return_state=True, **kw)
+        traj = [tuple(s["bbox"]) for s in st.search_path]
+        # un-sharded run in the same process
+        ref = RecordStub(hot)
+        fs2, pl2, ok2, av2, st2 = VS.visual_search(ref, img, "mug", None, smallest, scorer=NumpyScorer(), batch_size=8, return_state=True, **kw)
+        same_av = (av is None and av2 is None) or (av is not None and av2 is not None and torch.equal(av, av2))
+        cues = [s.get("context_cue", "") for s in st.search_path] == [s.get("context_cue", "") for s in st2.search_path]
+        # a node's heat map can be materialised on every rank although only its owner holds the mask (collective fetch)
+        hm_ok = True
+        if "final_heatmap" in st.search_path[0] and hot is None:
+            hm_ok = bool(np.array_equal(np.asarray(st.search_path[0]["final_heatmap"]), np.asarray(st2.search_path[0]["final_heatmap"])))
+        out.append((traj == [tuple(s["bbox"]) for s in st2.search_path], pl == pl2, inner.n_local, ref.n_local,
+                    torch.equal(fs["detection_result"], fs2["detection_result"]), same_av and cues and hm_ok, sh.gathered_bytes, sh.gathers,
+                    av.shape[0] if av is not None else -1))
+    q.put((rank, out))
     dist.destroy_process_group()
 
 
@@ -72,13 +61,19 @@ def test_sharded_frontier_world2_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    locals_ = []
-    for rank, same_traj, same_pl, n_local, n_ref, same_det in res:
-        assert same_traj and same_pl and same_det, (rank, same_traj, same_pl, same_det)
-        locals_.append(n_local)
-        total = n_ref
-    # the two ranks split the evaluations between them (speculative batches make the split uneven but complete)
-    assert sum(locals_) >= total and max(locals_) < total
+    by_rank = dict(res)
+    for case in range(3):
+        locals_ = []
+        for rank in (0, 1):
+            same_traj, same_pl, n_local, n_ref, same_det, same_rest, gathered, gathers, n_valid = by_rank[rank][case]
+            assert same_traj and same_pl and same_det and same_rest, (rank, case, by_rank[rank][case])
+            locals_.append(n_local)
+            total = n_ref
+            # fixed-size records: a few hundred floats per crop, not the 194 KB (2304 rows + 192^2 mask) of round 1
+            assert gathers >= 1 and gathered / max(1, sum(by_rank[0][case][2:3]) * 2) < 8192
+        # the two ranks split the evaluations between them (speculative batches make the split uneven but complete)
+        assert sum(locals_) >= total and max(locals_) < max(2, total)
+    assert by_rank[0][2][8] == 30            # the >16-valid-boxes follow-up broadcast delivered all 30 boxes on both ranks
 
 
 def _bcast_worker(rank, world, port, q):

@@ -39,8 +39,10 @@ SIGNATURES = {
     "vsb_flash_attn_bf16": [c_p, c_p, c_p, c_p, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
     "vsb_attn_set_impl": [c_i],
     "vsb_attn_small_bf16": [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
-    "vsb_owl_class_post": [c_p, c_ll, c_p, c_ll, c_i, c_ll, c_i, c_p, c_p, c_p],
-    "vsb_owl_box_post": [c_p, c_ll, c_p, c_i, c_ll, c_p, c_p],
+    "vsb_owl_class_post": [c_p, c_ll, c_p, c_ll, c_i, c_ll, c_i, c_i, c_p, c_p, c_p],
+    "vsb_owl_box_post": [c_p, c_ll, c_p, c_i, c_ll, c_i, c_p, c_p],
+    "vsb_pack_detections_f32": [c_p, c_p, c_i, c_i, c_p, c_ll, c_p],
+    "vsb_heat_pyramids_f32": [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_ll, c_p, c_p, c_p],
     "vsb_upsample2x_nhwc_bf16": [c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "vsb_im2col3x3_nhwc_bf16": [c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "vsb_mask_dot_bf16": [c_p, c_p, c_p, c_i, c_ll, c_i, c_p],

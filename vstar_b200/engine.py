@@ -192,11 +192,15 @@ class CropResult:
 class LlamaClipCore:
     """CLIP tower + Llama decoder on the sm_100a kernels with the fused-QKV cache; base of VSMEngine and VQAEngine."""
 
+    MAX_POSITIONS = 2048          # rows of the RoPE tables (Llama-1 / Vicuna max_position_embeddings)
+
     def __init__(self, weights: CoreWeights, max_batch=8, max_tokens=384):
         self.w = weights
         self.cfg = weights.cfg
         self.dev = weights.device
-        self.max_tokens = max_tokens
+        # rows per KV-cache slot allocated up front; the cache GROWS (up to MAX_POSITIONS) when a prompt or a generation
+        # needs more - nothing is truncated silently, and a sequence beyond the RoPE tables raises VsbError
+        self.max_tokens = min(int(max_tokens), self.MAX_POSITIONS)
         self._cache = None
         self._cache_shape = None
         self._layer_table = None        # ctypes array of per-layer weight pointers for the native layer runner
@@ -204,6 +208,9 @@ class LlamaClipCore:
         # shared-prefix KV (see prefill): the text before <im_start> is the same for every crop
         self.prefix_cache = True
         self.tail_only = os.environ.get("VSB_TAIL_ONLY", "1") != "0"    # last layer over the consumed rows only (draft-verify path)
+        # detection logits / scores / boxes rounded to bf16 VALUES like the reference's bf16 model emits them, so thresholds,
+        # argmax ties and all_valid_boxes are decided on the same numbers (visual_search.py:399-409); False = full fp32 heads
+        self.heads_bf16 = True
         self._prefix_ids = None          # tuple of token ids
         self._prefix_kv = None           # [n_layers, P, 3d] snapshot of the cache rows of that prefix
         self._prefix_slots = 0           # cache slots whose rows 0..P currently hold it
@@ -247,14 +254,29 @@ class LlamaClipCore:
         return ops.owl_merge(x, o["post_w"], o["post_b"], o["merge_w"], o["merge_b"], images.shape[0], S, c.vit_eps)
 
     # ------------------------------------------------------------------ LLM
-    def _ensure_cache(self, B, Tmax):
+    def _capacity(self, need):
+        """rows per cache slot for a sequence of `need` positions: at least self.max_tokens, multiples of 64"""
+        if need > self.MAX_POSITIONS:
+            raise ops._lib.VsbError(f"sequence of {need} positions exceeds the {self.MAX_POSITIONS} rows of the RoPE tables "
+                                    "(max_position_embeddings of the Llama-1/Vicuna backbone)")
+        return min(self.MAX_POSITIONS, max(self.max_tokens, (need + 63) // 64 * 64))
+
+    def _ensure_cache(self, B, Tmax, keep=False):
+        """cache with >= B slots of >= Tmax rows.  keep=True preserves the rows already written (decode-time growth)."""
         c = self.cfg
+        cur = self._cache_shape
+        if self._cache is not None and cur[1] >= B and cur[2] >= Tmax:
+            return self._cache
+        if cur is not None:
+            B, Tmax = max(B, cur[1]), max(Tmax, cur[2])
         shape = (c.n_layers, B, Tmax, 3 * c.hidden)
-        if self._cache is None or self._cache_shape[1] < B or self._cache_shape[2] < Tmax:
-            self._cache = None
-            self._cache = torch.empty(shape, dtype=BF, device=self.dev)
-            self._cache_shape = shape
-            self._prefix_slots = 0
+        old = self._cache if keep else None
+        self._cache = None                                # release before allocating the replacement (unless kept)
+        self._cache = torch.empty(shape, dtype=BF, device=self.dev)
+        if old is not None:
+            self._cache[:, :cur[1], :cur[2]].copy_(old)
+        self._cache_shape = shape
+        self._prefix_slots = 0
         return self._cache
 
     def _llm_layers(self, x, B, Tn, past, Tmax, positions=None, k_start=None, cache_row_offset=0, tail_rows=0):
@@ -285,9 +307,10 @@ class LlamaClipCore:
         assert pos >= self._P, "position inside the shared prefix: its rows are not recomputed"
         return b * self._Tn + pos - self._P
 
-    def prefill(self, input_ids, images_clip, tail_rows=0):
+    def prefill(self, input_ids, images_clip, tail_rows=0, reserve=0):
         """input_ids int64 [B, L] (same L and same image position for the whole batch), images_clip [B,3,224,224] bf16.
         tail_rows > 0: the caller reads only the last tail_rows positions of every crop (see vsb_llama_layers).
+        reserve: positions the caller will append by decoding (the cache slot is sized for T + reserve up front).
         Returns (x, T, img_pos): the residual stream (pre final norm) of the rows that were computed, the spliced length T
         and the image position.  Use x_row(b, pos) to address x.
 
@@ -307,9 +330,8 @@ class LlamaClipCore:
         assert bool((input_ids[:, img_pos] == IMAGE_TOKEN_INDEX).all())
         n_img = c.clip_tokens
         T = L - 1 + n_img
-        assert T <= self.max_tokens
         assert img_pos >= 1
-        self._ensure_cache(B, self.max_tokens)
+        self._ensure_cache(B, self._capacity(T + reserve))
         # P = rows before the <im_start> slot (the CLS row of the projector GEMM lands on that slot, see below)
         P = 0
         if self.prefix_cache and img_pos >= 2:
@@ -335,18 +357,23 @@ class LlamaClipCore:
                 self._prefix_slots = B
             self.stats["prefix_shared"] += B
         self._llm_layers(x, B, Tn, P, self.max_tokens, tail_rows=tail_rows if self.tail_only else 0)
-        if not P and self.prefix_cache and img_pos >= 2 and self._prefix_ids is None:
-            head = input_ids[:, :img_pos - 1]
-            if bool((head == head[0]).all()):
-                self._prefix_ids = tuple(head[0].tolist())
-                self._prefix_kv = self._cache[:, 0, :img_pos - 1].clone()
-                self._prefix_slots = B                  # every slot of this batch just computed the same rows
+        if not P:
+            # a full prefill has just overwritten rows 0.. of slots 0..B-1: whatever prefix they held is gone
+            self._prefix_slots = 0
+            if self.prefix_cache and img_pos >= 2 and self._prefix_ids is None:
+                head = input_ids[:, :img_pos - 1]
+                if bool((head == head[0]).all()):
+                    self._prefix_ids = tuple(head[0].tolist())
+                    self._prefix_kv = self._cache[:, 0, :img_pos - 1].clone()
+                    self._prefix_slots = B              # every slot of this batch just computed the same rows
         self._P, self._Tn = P, Tn
         return x, T, img_pos
 
     def decode_step(self, tokens, B, past):
         """one greedy step for B sequences that all have `past` cached positions; tokens int64 [B] -> next argmax [B]"""
         c = self.cfg
+        if past + 1 > self._cache_shape[2]:
+            self._ensure_cache(self._cache_shape[1], self._capacity(past + 64), keep=True)
         x = ops.gather_rows(tokens.contiguous(), self.w.embed)
         self._llm_layers(x, B, 1, past, self.max_tokens)
         hn = ops.rmsnorm(x, self.w.final_norm, c.rms_eps)
@@ -438,13 +465,13 @@ class VSMEngine(LlamaClipCore):
         hb = ops.gemm(fmap, w.box[0][0], bias=w.box[0][1], epilogue=ops.EPI_GELU)
         hb = ops.gemm(hb, w.box[1][0], bias=w.box[1][1], epilogue=ops.EPI_GELU)
         yb = ops.gemm(hb, w.box[2][0], bias=w.box[2][1], out_dtype=torch.float32)
-        boxes = ops.owl_box_post(yb, w.box_bias, P).view(B, P, 4)
+        boxes = ops.owl_box_post(yb, w.box_bias, P, quant_bf16=self.heads_bf16).view(B, P, 4)
         if crop_of_loc == list(range(B)):
-            logits, scores = ops.owl_class_post(y, det_q.contiguous(), P, Q)
+            logits, scores = ops.owl_class_post(y, det_q.contiguous(), P, Q, quant_bf16=self.heads_bf16)
             return logits.view(n, P), scores.view(n, P), boxes          # one entry per crop: boxes [n,P,4] with n == B
         idx = torch.tensor(crop_of_loc, device=self.dev)
         yy = y.view(B, P, Q + 2).index_select(0, idx).reshape(n * P, Q + 2).contiguous()
-        logits, scores = ops.owl_class_post(yy, det_q.contiguous(), P, Q)
+        logits, scores = ops.owl_class_post(yy, det_q.contiguous(), P, Q, quant_bf16=self.heads_bf16)
         return logits.view(n, P), scores.view(n, P), boxes.index_select(0, idx)
 
     # ------------------------------------------------------------------ whole-model entry points
@@ -481,11 +508,12 @@ class VSMEngine(LlamaClipCore):
             out["pred_logits"], out["scores"], out["pred_boxes"] = self.owl_heads(fmap, det_q, crop_of_loc)
         return out
 
-    def finish(self, out):
-        """resolve a deferred inference(): the one host sync (greedy argmax of the answer rows vs the draft)"""
+    def finish(self, out, am_host=None):
+        """resolve a deferred inference(): the one host sync (greedy argmax of the answer rows vs the draft).  am_host: the
+        argmax tensor already copied to the host by the caller (pipelined batches fetch it on a side stream)."""
         if out.get("verified") is None:
             am, draft, B = out.pop("_am"), out.pop("_draft"), out["n_crops"]
-            am = am.view(B, -1).cpu()
+            am = (am_host if am_host is not None else am.cpu()).view(B, -1)
             ok = [bool((am[b] == draft).all()) for b in range(B)] if not out.pop("_forced") else [True] * B
             self.last_argmax = am
             self.stats["fallback"] += sum(1 for o in ok if not o)
@@ -538,7 +566,9 @@ class VSMEngine(LlamaClipCore):
         mathematically the same sequence).  Returns (output_ids list, per-step argmax list, residual rows)."""
         c = self.cfg
         assert prompt_ids.shape[0] == 1
-        x, T, img_pos = self.prefill(prompt_ids.to(self.dev), images_clip)
+        L = prompt_ids.shape[1]
+        room = self.MAX_POSITIONS - (L - 1 + c.clip_tokens)
+        x, T, img_pos = self.prefill(prompt_ids.to(self.dev), images_clip, reserve=max(0, min(max_new_tokens, room)))
         last = torch.tensor([self.x_row(0, T - 1)], dtype=torch.int64, device=self.dev)
         hn, am, logits = self._logits_rows(x, last)
         out = prompt_ids[0].cpu().tolist()
@@ -550,7 +580,7 @@ class VSMEngine(LlamaClipCore):
             if forced_ids is not None and step < len(forced_ids):
                 nxt = int(forced_ids[step])
             out.append(nxt)
-            if nxt == eos_token_id or step == max_new_tokens - 1 or past >= self.max_tokens:
+            if nxt == eos_token_id or step == max_new_tokens - 1:
                 break
             am, hn, logits = self.decode_step(torch.tensor([nxt], dtype=torch.int64, device=self.dev), 1, past)
             past += 1

@@ -270,24 +270,74 @@ def attn_small(q, k, v, B, H, Nq, Nk, D, scale, out=None):
     return out
 
 
-def owl_class_post(y, query, rows_per_crop, Q):
+def owl_class_post(y, query, rows_per_crop, Q, quant_bf16=False):
+    """quant_bf16: round logits / scores to bf16 values (what the reference's bf16 model emits), fp32 storage"""
     _chk(y, torch.float32), _chk(query, BF16)
     R = y.shape[0]
     logits = torch.empty((R,), dtype=torch.float32, device=y.device)
     scores = torch.empty((R,), dtype=torch.float32, device=y.device)
     _lib.launches += 1
-    call("vsb_owl_class_post", y.data_ptr(), y.stride(0), query.data_ptr(), query.stride(0), rows_per_crop, R, Q, logits.data_ptr(),
-         scores.data_ptr(), _stream())
+    call("vsb_owl_class_post", y.data_ptr(), y.stride(0), query.data_ptr(), query.stride(0), rows_per_crop, R, Q, 1 if quant_bf16 else 0,
+         logits.data_ptr(), scores.data_ptr(), _stream())
     return logits, scores
 
 
-def owl_box_post(y, box_bias, rows_per_crop):
+def owl_box_post(y, box_bias, rows_per_crop, quant_bf16=False):
     _chk(y, torch.float32), _chk(box_bias, torch.float32)
     R = y.shape[0]
     boxes = torch.empty((R, 4), dtype=torch.float32, device=y.device)
     _lib.launches += 1
-    call("vsb_owl_box_post", y.data_ptr(), y.stride(0), box_bias.data_ptr(), rows_per_crop, R, boxes.data_ptr(), _stream())
+    call("vsb_owl_box_post", y.data_ptr(), y.stride(0), box_bias.data_ptr(), rows_per_crop, R, 1 if quant_bf16 else 0, boxes.data_ptr(),
+         _stream())
     return boxes
+
+
+def pack_detections(scores, boxes, rec, row0=0):
+    """scores fp32 [n,P], boxes fp32 [n,P,4] -> records rec[row0 : row0+n] (fields 0..7 and 12..75, see records.py)"""
+    _chk(scores, torch.float32), _chk(boxes, torch.float32), _chk(rec, torch.float32)
+    n, P = scores.shape
+    assert scores.is_contiguous() and boxes.is_contiguous() and boxes.shape == (n, P, 4)
+    assert rec.dim() == 2 and rec.is_contiguous() and row0 + n <= rec.shape[0]
+    _lib.launches += 1
+    call("vsb_pack_detections_f32", scores.data_ptr(), boxes.data_ptr(), n, P, rec.data_ptr() + row0 * rec.shape[1] * 4, rec.shape[1],
+         _stream())
+    return rec
+
+
+def heat_pyramids(jobs, rec, LH, LW):
+    """jobs: list of (low_res fp32 [LH,LW] device view, h, w, rects [(x,y,w,h) relative to the crop], record row).
+    Fills the heat-map statistics and rectangle sums of those records straight from the low-res masks (no H x W map)."""
+    import numpy as np
+    if not jobs:
+        return rec
+    _chk(rec, torch.float32)
+    R = rec.shape[1]
+    nj = len(jobs)
+    total = sum(len(j[3]) for j in jobs)
+    table = np.zeros(nj * 8 + total * 5, dtype=np.int32)
+    jt = table[:nj * 8].reshape(nj, 8)
+    rt = table[nj * 8:nj * 8 + total * 4].reshape(total, 4)
+    rj = table[nj * 8 + total * 4:]
+    off = 0
+    for k, (low, h, w, rects, row) in enumerate(jobs):
+        assert low.dtype == torch.float32 and low.is_cuda and low.is_contiguous() and low.shape[-2:] == (LH, LW)
+        assert len(rects) <= R - 76, (len(rects), R)
+        p = low.data_ptr()
+        jt[k] = (0, 0, h, w, off, len(rects), row, 0)
+        jt[k, 0:2] = np.array([p], dtype=np.uint64).view(np.int32)
+        if rects:
+            rt[off:off + len(rects)] = np.asarray(rects, dtype=np.int32)
+            rj[off:off + len(rects)] = k
+        off += len(rects)
+    dev = rec.device
+    tab = torch.from_numpy(table).to(dev, non_blocking=True)
+    stats_scratch = torch.empty((nj * 64 * 3,), dtype=torch.float32, device=dev)
+    rect_scratch = torch.empty((max(1, total) * 64,), dtype=torch.float64, device=dev)
+    base = tab.data_ptr()
+    _lib.launches += 2 + (2 if total else 0)
+    call("vsb_heat_pyramids_f32", base, nj, base + nj * 32, base + nj * 32 + total * 16, total, LH, LW, rec.data_ptr(), R,
+         stats_scratch.data_ptr(), rect_scratch.data_ptr(), _stream())
+    return rec
 
 
 def upsample2x_nhwc(x, B, H, W, C):

@@ -1,94 +1,161 @@
 """Frontier sharding over the GPUs of one box: SPMD control, data-parallel crop evaluation.
 
-Every rank runs the SAME search controller on the SAME search images (deterministic host code), so no decision ever
-has to be broadcast.  Only `detect_regions` is distributed: the frontier batch is dealt round-robin over the ranks, each
-rank evaluates its share with its own replica of the weights, and one fixed-size record per crop — top score, top box,
-all 2304 (score, box) rows and the 192x192 low-res mask (194 KB) — is all-gathered (NCCL over NVLink / NVSwitch; gloo in
-the CPU tests) so that every rank holds every result and commits nodes in the reference's pop order.  This is the only
-exchange step on the path; there is no reduction and no tensor parallelism.
+Every rank runs the SAME search controller on the SAME search images (deterministic host code), so no decision ever has to
+be broadcast.  Only the batched crop evaluation is distributed: a frontier batch is dealt round-robin over the ranks, each
+rank evaluates its share with its own replica of the weights and produces one fixed-size CROP RECORD per crop on the device
+(records.py: best score/box, boxes above 0.5, heat-map statistics, rectangle sums of the normalised map over the crop's
+quad-tree descendants; 76 + #rectangles floats ~ 0.3-1.7 KB, 5.5 KB for the root of an 8192^2 / 256 search).  ONE
+`all_gather_into_tensor` of those records per batch (NCCL over NVLink / NVSwitch; gloo in the CPU tests) gives every rank
+every result; nodes are then committed in the reference's pop order on all ranks alike.  The 192 x 192 masks stay on the rank
+that computed them (the controller never needs them: the rectangle sums are in the record); `search_path[i]['final_heatmap']`
+of a node owned by another rank is fetched by a broadcast only if somebody materialises it (visualisation).
+There is no reduction, no tensor parallelism and no per-record host synchronisation on this path.
 """
 from __future__ import annotations
 
 import torch
 import torch.distributed as dist
 
+from .records import pyramid_rects, record_floats
 from .visual_search import _NodeEval
 
 
 class ShardedVSM:
+    """Wraps a local VSM replica (anything with detect_regions_launch / detect_regions_finish producing record tensors)."""
+
     def __init__(self, vsm, group=None, device=None):
         self.vsm = vsm
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.device = device
+        self.device = device if device is not None else getattr(getattr(vsm, "engine", None), "dev", "cpu")
         self.frontier_batch = getattr(vsm, "frontier_batch", 8) * self.world
-        self.gathered_bytes = 0
+        self.gathered_bytes = 0          # bytes this rank received through the record all-gathers
+        self.gathers = 0
+        self._bufs = {}
+        self._d2h_stream = None
 
     # everything that is not the batched detection goes to the local replica (vqa / segmentation of the weak-cue branch
     # are pure functions of the crop, so every rank computes the same value)
     def inference(self, image, question, mode="segmentation"):
         return self.vsm.inference(image, question, mode)
 
-    @staticmethod
-    def _pack(ev, P, L):
-        rec = torch.zeros(6 + 5 * P + L, dtype=torch.float32, device=ev.low_res.device)
-        rec[0] = float(ev.top_logit)
-        rec[1:5] = ev.top_box.to(rec.device)
-        rec[5] = float(ev.n_logits)
-        rec[6:6 + P] = ev.scores.reshape(-1).to(rec.device)
-        rec[6 + P:6 + 5 * P] = ev.boxes.reshape(-1).to(rec.device)
-        rec[6 + 5 * P:] = ev.low_res.reshape(-1)
-        return rec
+    def _buffer(self, name, shape, dtype, pinned=False):
+        key = (name, tuple(shape), dtype)
+        b = self._bufs.get(key)
+        if b is None:
+            if pinned:
+                b = torch.empty(shape, dtype=dtype).pin_memory()
+            else:
+                b = torch.empty(shape, dtype=dtype, device=self.device)
+            self._bufs[key] = b
+        return b
 
-    @staticmethod
-    def _unpack(rec, P, side):
-        ev = _NodeEval()
-        host = rec[:6].cpu()
-        ev.top_logit = float(host[0])
-        ev.top_box = host[1:5].clone()
-        ev.n_logits = int(host[5])
-        ev.scores = rec[6:6 + P].view(P, 1)
-        ev.boxes = rec[6 + P:6 + 5 * P].view(P, 4)
-        ev.low_res = rec[6 + 5 * P:].view(side, side)
-        return ev
-
-    def detect_regions(self, regions, questions):
-        n = len(regions)
-        w, r = self.world, self.rank
+    def detect_regions_launch(self, regions, questions, smallest_sizes):
+        n, w, r = len(regions), self.world, self.rank
         mine = list(range(r, n, w))
-        evs = self.vsm.detect_regions([regions[i] for i in mine], [questions[i] for i in mine]) if mine else []
         n_max = (n + w - 1) // w
-        # record geometry from the first local result; ranks without work learn it from the gathered header
-        if evs:
-            P = evs[0].scores.numel()
-            side = evs[0].low_res.shape[-1]
-            dev = evs[0].low_res.device
+        # the record length is a function of the batch's geometry only, so every rank computes the same value
+        R = record_floats(max(len(pyramid_rects(b, ss)) for (_, b), ss in zip(regions, smallest_sizes)))
+        local = self.vsm.detect_regions_launch([regions[i] for i in mine], [questions[i] for i in mine],
+                                               [smallest_sizes[i] for i in mine], rec_len=R) if mine else None
+        cuda = torch.device(self.device).type == "cuda"
+        # double-buffered by launch parity: with two batches in flight the previous gather's buffers are still being read
+        slot = self.gathers % 4
+        send = self._buffer(("send", slot), (n_max, R), torch.float32)
+        recv = self._buffer(("recv", slot), (w * n_max, R), torch.float32)
+        if local is not None:
+            rec = local["rec"]
+            send[:rec.shape[0]].copy_(rec)
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        self.gathers += 1
+        self.gathered_bytes += recv.numel() * 4
+        pend = dict(n=n, mine=mine, local=local, regions=regions, smallest=list(smallest_sizes), recv=recv, n_max=n_max, R=R, done=None)
+        if cuda:
+            main = torch.cuda.current_stream()
+            ready = torch.cuda.Event()
+            ready.record(main)
+            if self._d2h_stream is None:
+                self._d2h_stream = torch.cuda.Stream(device=self.device)
+            host = self._buffer(("host", slot), (w * n_max, R), torch.float32, pinned=True)
+            with torch.cuda.stream(self._d2h_stream):
+                self._d2h_stream.wait_event(ready)
+                host.copy_(recv, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(self._d2h_stream)
+            pend["host"], pend["done"] = host, done
         else:
-            P, side, dev = 0, 0, self.device
-        geo = torch.tensor([P, side], dtype=torch.int64, device=dev)
-        dist.all_reduce(geo, op=dist.ReduceOp.MAX, group=self.group)
-        P, side = int(geo[0]), int(geo[1])
-        L = side * side
-        mine_rec = torch.zeros((n_max, 6 + 5 * P + L), dtype=torch.float32, device=dev)
-        for k, ev in enumerate(evs):
-            mine_rec[k] = self._pack(ev, P, L)
-        parts = [torch.empty_like(mine_rec) for _ in range(w)]
-        dist.all_gather(parts, mine_rec, group=self.group)
-        self.gathered_bytes += mine_rec.numel() * 4 * w
+            pend["host"] = recv
+        return pend
+
+    def detect_regions_finish(self, pend):
+        if pend["done"] is not None:
+            pend["done"].synchronize()
+        rows = pend["host"].numpy()
+        w, n_max = self.world, pend["n_max"]
+        own = {}
+        if pend["local"] is not None:
+            # local finish: resolves this rank's draft verification and hands back the device-side tensors of its own crops
+            for i, ev in zip(pend["mine"], self.vsm.detect_regions_finish(pend["local"])):
+                own[i] = ev
         out = []
-        for i in range(n):
-            out.append(self._unpack(parts[i % w][i // w], P, side))
+        for i in range(pend["n"]):
+            ev = _NodeEval.from_record(rows[(i % w) * n_max + i // w], pend["regions"][i][1], pend["smallest"][i])
+            src = i % w
+            mine = own.get(i)
+            # masks / detections stay with their owner; the two fetchers are COLLECTIVE (every rank calls them at the same
+            # point of the same controller), so ev.low_res is left unset even on the owning rank
+            ev.fetch_valid = self._valid_fetcher(mine, src)
+            ev.fetch_low_res = self._low_res_fetcher(mine, src)
+            out.append(ev)
         return out
 
+    def detect_regions(self, regions, questions, smallest_sizes=None):
+        if smallest_sizes is None:
+            smallest_sizes = [max(1, min(int(b[2]), int(b[3])) // 2) for _, b in regions]
+        return self.detect_regions_finish(self.detect_regions_launch(regions, questions, smallest_sizes))
 
-def broadcast_loader(get, src=0, group=None, device="cuda"):
+    # -- rare follow-ups (SPMD: every rank reaches them at the same point of the same controller) ---------------------
+    def _valid_fetcher(self, mine, src):
+        """more than 16 boxes above 0.5 at a successful ROOT (visual_search.py:406-410): the owner broadcasts the full list"""
+
+        def fetch():
+            n = torch.zeros(1, dtype=torch.int64, device=self.device)
+            if mine is not None:
+                boxes = mine.fetch_valid().to(self.device).float().contiguous()
+                n[0] = boxes.shape[0]
+            dist.broadcast(n, src=src, group=self.group)
+            if mine is None:
+                boxes = torch.empty((int(n[0]), 4), dtype=torch.float32, device=self.device)
+            dist.broadcast(boxes, src=src, group=self.group)
+            return boxes.cpu()
+
+        return fetch
+
+    def _low_res_fetcher(self, mine, src):
+        def fetch():
+            shape = torch.zeros(2, dtype=torch.int64, device=self.device)
+            if mine is not None:
+                low = mine.low_res.to(self.device).float().contiguous()
+                shape[0], shape[1] = low.shape[-2], low.shape[-1]
+            dist.broadcast(shape, src=src, group=self.group)
+            if mine is None:
+                low = torch.empty((int(shape[0]), int(shape[1])), dtype=torch.float32, device=self.device)
+            dist.broadcast(low, src=src, group=self.group)
+            return low
+
+        return fetch
+
+
+def broadcast_loader(get, src=0, group=None, device="cuda", bucket_bytes=256 << 20):
     """Weight broadcast at start-up: only rank `src` reads the checkpoint; every rank builds its replica
     through the returned `name -> tensor` callable, which on `src` loads the tensor and broadcasts it (NCCL over NVLink on
     the GPUs, gloo on CPU) and elsewhere receives it.  All ranks must request the same names in the same order - which they
     do, because `CoreWeights` / `VSMWeights` / `VQAWeights` walk the reference's key layout deterministically.
-    `get` may be None on the other ranks."""
+    `get` may be None on the other ranks.  `load.stats` counts tensors / bytes / seconds spent in the broadcasts."""
+    import time
     rank = dist.get_rank(group)
+    stats = dict(tensors=0, bytes=0, seconds=0.0)
 
     def load(name):
         if rank == src:
@@ -101,7 +168,12 @@ def broadcast_loader(get, src=0, group=None, device="cuda"):
         if rank != src:
             t = torch.empty(shape, dtype=dtype, device=device)
         t = t.contiguous()
+        t0 = time.perf_counter()
         dist.broadcast(t, src=src, group=group)
+        stats["seconds"] += time.perf_counter() - t0
+        stats["tensors"] += 1
+        stats["bytes"] += t.numel() * t.element_size()
         return t
 
+    load.stats = stats
     return load

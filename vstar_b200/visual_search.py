@@ -10,8 +10,13 @@ What is different underneath (B200-first):
   * frontier nodes are evaluated SPECULATIVELY in batches (each node's outputs are a pure function of its crop) and
     committed strictly in pop order; speculative work is simply dropped when the search ends early;
   * several searches can run in lock-step (`visual_search_many`) so their frontiers share one GPU batch;
-  * heatmap statistics and the ancestor-chain sub-patch sums run on the GPU (ops.heatmap / ops.rect_sums); only a
-    handful of scalars cross PCIe per expansion instead of the H x W fp32 map (visual_search.py:448).
+  * every crop evaluation comes back as ONE fixed-size record (records.py): best score/box, the boxes above 0.5, the
+    heat-map statistics and the sums of the normalised map over the crop's quad-tree descendants — computed on the GPU
+    straight from the 192 x 192 low-res mask.  Committing a node is then pure host arithmetic on records of the node
+    and its ancestors: no H x W map is written, copied (visual_search.py:448) or re-read per expansion, and nothing
+    synchronises with the GPU between the arrival of a batch and the launch of the next one;
+  * batches are PIPELINED: while one frontier batch runs on the GPU the controller commits the previous one and
+    launches the next (`depth` batches in flight), so the GPU does not idle across the host's commit phase.
 """
 from __future__ import annotations
 
@@ -69,27 +74,9 @@ def refine_bbox(bbox, image_width, image_height):
     return bbox
 
 
-def split_4subpatches(current_patch_bbox):
-    hw_ratio = current_patch_bbox[3] / current_patch_bbox[2]
-    if hw_ratio >= 2:
-        return 1, 4
-    elif hw_ratio <= 0.5:
-        return 4, 1
-    else:
-        return 2, 2
-
-
-def get_sub_patches(current_patch_bbox, num_of_width_patches, num_of_height_patches):
-    width_stride = int(current_patch_bbox[2] // num_of_width_patches)
-    height_stride = int(current_patch_bbox[3] / num_of_height_patches)
-    sub_patches = []
-    for j in range(num_of_height_patches):
-        for i in range(num_of_width_patches):
-            sub_patch_width = current_patch_bbox[2] - i * width_stride if i == num_of_width_patches - 1 else width_stride
-            sub_patch_height = current_patch_bbox[3] - j * height_stride if j == num_of_height_patches - 1 else height_stride
-            sub_patches.append([current_patch_bbox[0] + i * width_stride, current_patch_bbox[1] + j * height_stride,
-                                sub_patch_width, sub_patch_height])
-    return sub_patches, width_stride, height_stride
+# split_4subpatches / get_sub_patches (visual_search.py:234-253) live in records.py (the record layout is defined by the same
+# quad-tree geometry) and are re-exported here under the reference's names
+from .records import expandable, get_sub_patches, parse_record, pyramid_rects, split_4subpatches  # noqa: E402,F401
 
 
 def iou(bbox1, bbox2):
@@ -174,6 +161,62 @@ class CudaScorer:
         return res
 
 
+class MapPyramid:
+    """rectangle sums of a node's normalised map computed on demand from a materialised Heatmap (generic vsm objects that
+    return the H x W map, and the weak-cue branch whose map comes from a second inference)"""
+
+    def __init__(self, scorer, heat, bbox):
+        self.scorer, self.heat, self.bbox = scorer, heat, [int(v) for v in bbox]
+        self.sums = {}
+
+    @property
+    def stats(self):
+        return self.heat.host_stats()
+
+    def missing(self, rects):
+        return [r for r in rects if r not in self.sums]
+
+    def relative(self, rects):
+        return [[r[0] - self.bbox[0], r[1] - self.bbox[1], r[2], r[3]] for r in rects]
+
+    def get(self, rect):
+        return self.sums[rect]
+
+
+def fill_pyramids(scorer, wanted):
+    """wanted: list of (pyramid, rects).  All sums that are not in a record come from ONE scorer.rect_sums call (one sync)."""
+    jobs = [(p, p.missing(rects)) for p, rects in wanted]
+    jobs = [(p, m) for p, m in jobs if m]
+    if not jobs:
+        return
+    res = scorer.rect_sums([(p.heat, p.relative(m)) for p, m in jobs])
+    for (p, m), vals in zip(jobs, res):
+        for r, v in zip(m, vals):
+            p.sums[r] = v
+
+
+class LazyHeat:
+    """search_path[i]['final_heatmap'] without paying for it: the reference stores normalize_score(map) as a [h,w,1] fp32
+    numpy array per expanded node (visual_search.py:448) although only the visualiser reads it; here the array is
+    materialised from the node's low-res mask when somebody converts it (np.asarray)."""
+
+    def __init__(self, scorer, low_res, h, w, fetch=None):
+        self.scorer, self.low_res, self.h, self.w, self.fetch = scorer, low_res, h, w, fetch
+        self._heat = None
+
+    def heat(self):
+        if self._heat is None:
+            low = self.low_res if self.low_res is not None else (self.fetch() if self.fetch is not None else None)
+            if low is None:
+                raise RuntimeError("this node's low-res mask lives on another rank (sharded frontier) and was not fetched")
+            self._heat = self.scorer.from_low_res(low, self.h, self.w)
+        return self._heat
+
+    def __array__(self, dtype=None, copy=None):
+        a = np.asarray(self.heat())
+        return a.astype(dtype) if dtype is not None else a
+
+
 def _sub_scores_from_sums(sums, n_children):
     """get_subpatch_scores (visual_search.py:255-266) given rectangle sums of the normalised map: sums[:n] children,
     sums[n] whole patch.  Arithmetic in numpy float32 like the reference's `.sum()` results."""
@@ -194,17 +237,35 @@ def _sub_scores_from_sums(sums, n_children):
 # ---------------------------------------------------------------------------------------------------------------
 class _NodeEval:
     """Outputs of one detection-mode evaluation of a crop, reduced to what the controller consumes."""
-    __slots__ = ("top_logit", "top_box", "n_logits", "boxes", "scores", "low_res", "full_map", "heat")
+    __slots__ = ("top_logit", "top_box", "n_logits", "boxes", "scores", "low_res", "full_map", "heat", "pyramid", "n_valid",
+                 "valid_boxes", "fetch_valid", "fetch_low_res")
 
     def __init__(self):
         self.top_logit = None    # python float (sigmoid score)
         self.top_box = None      # torch CPU float32 [4] cxcywh in (0,1)
         self.n_logits = 0
-        self.boxes = None        # full [P,4] (kept on device / lazily fetched; needed only for the root success case)
+        self.boxes = None        # full [P,4] (device; needed only when the record's 16 valid boxes overflow)
         self.scores = None
-        self.low_res = None      # [4g,4g] fp32 device
+        self.low_res = None      # [4g,4g] fp32 device (None for crops evaluated by another rank)
         self.full_map = None     # H x W tensor from a generic vsm.inference
         self.heat = None         # Heatmap once materialised
+        self.pyramid = None      # RecordPyramid (record path) - None for generic vsm objects
+        self.n_valid = None      # rows with score > 0.5 (record path)
+        self.valid_boxes = None  # torch CPU [min(n_valid,16), 4] cxcywh (record path)
+        self.fetch_valid = None  # callable -> all valid boxes, for n_valid > 16 (owner rank's device copy / broadcast)
+        self.fetch_low_res = None
+
+    @classmethod
+    def from_record(cls, row, bbox, smallest_size):
+        r = parse_record(row, bbox, smallest_size)
+        if r["top_index"] < 0:
+            raise RuntimeError("crop evaluation produced no finite detection score (NaN logits)")
+        ev = cls()
+        ev.top_logit, ev.n_logits, ev.n_valid = r["top_logit"], r["n_logits"], r["n_valid"]
+        ev.top_box = torch.from_numpy(r["top_box"])
+        ev.valid_boxes = torch.from_numpy(r["valid_boxes"])
+        ev.pyramid = r["pyramid"]
+        return ev
 
 
 class SearchState:
@@ -220,6 +281,7 @@ class SearchState:
         self.queue = PriorityQueue()
         self.current = init_patch
         self.cache = {}               # bbox tuple -> _NodeEval
+        self.pending = set()          # bbox tuples whose evaluation is in flight
         self.done = False
         self.success = False
         self.all_valid_boxes = None
@@ -230,18 +292,23 @@ class SearchState:
     def key(patch):
         return tuple(int(v) for v in patch["bbox"])
 
+    def _free(self, patch):
+        k = self.key(patch)
+        return k not in self.cache and k not in self.pending
+
     def wanted(self, k):
-        """Nodes whose evaluation is (or is likely to be) needed next: the current node first, then the best k-1 queue
-        entries (speculation; does not touch the heap order)."""
+        """Nodes whose evaluation is (or is likely to be) needed next and is neither cached nor in flight: the current node
+        first, then the best queue entries (speculation; does not touch the heap order)."""
         out = []
-        if not self.done and self.key(self.current) not in self.cache:
+        if self.done or k <= 0:
+            return out
+        if self._free(self.current):
             out.append(self.current)
-        if k > len(out) and not self.done:
-            rest = sorted(self.queue.queue)
-            for pr in rest:
+        if k > len(out):
+            for pr in sorted(self.queue.queue):
                 if len(out) >= k:
                     break
-                if self.key(pr.item) not in self.cache and all(pr.item is not o for o in out):
+                if self._free(pr.item) and all(pr.item is not o for o in out):
                     out.append(pr.item)
         return out
 
@@ -251,21 +318,50 @@ class SearchState:
 
 
 class SearchController:
-    """Runs one or many SearchStates against a vsm object, batching node evaluations."""
+    """Runs one or many SearchStates against a vsm object, batching (and pipelining) node evaluations."""
 
-    def __init__(self, vsm, scorer=None, batch_size=1, extract_noun_chunks=None):
+    def __init__(self, vsm, scorer=None, batch_size=1, extract_noun_chunks=None, depth=2, split_min=8):
         self.vsm = vsm
         self.scorer = scorer if scorer is not None else CudaScorer()
         self.batch_size = max(1, int(batch_size))
+        if extract_noun_chunks is None:
+            # the reference always parses the location phrase with spaCy (visual_search.py:435); the default here does the
+            # same and RAISES if spaCy is missing rather than silently using "region {phrase}" for every node
+            from .noun_chunks import extract_noun_chunks as _enc
+            extract_noun_chunks = _enc
         self.extract_noun_chunks = extract_noun_chunks
         self.regions = hasattr(vsm, "detect_regions")
         self.batched = self.regions or hasattr(vsm, "detect_batch")
+        self.pipelined = hasattr(vsm, "detect_regions_launch")
+        self.depth = max(1, int(depth))
+        self.split_min = split_min
+        self.batches = []              # sizes of the launched batches (diagnostics)
 
     # -- evaluation ----------------------------------------------------------------------------------------
+    def _launch(self, requests):
+        """asynchronous: the GPU work of the batch is queued, nothing is waited for"""
+        for st, p in requests:
+            st.pending.add(st.key(p))
+        questions = [DETECTION_QUESTION.format(st.target) for st, p in requests]
+        handle = self.vsm.detect_regions_launch([(st.image, p["bbox"]) for st, p in requests], questions,
+                                                [st.smallest_size for st, p in requests])
+        self.batches.append(len(requests))
+        return requests, handle
+
+    def _collect(self, inflight):
+        requests, handle = inflight
+        results = self.vsm.detect_regions_finish(handle)
+        for (st, p), ev in zip(requests, results):
+            k = st.key(p)
+            st.pending.discard(k)
+            st.cache[k] = ev
+            st.n_evals += 1
+
     def _evaluate(self, requests):
-        """requests: list of (state, patch).  Fills state.cache."""
+        """synchronous evaluation (vsm objects without the launch/finish API).  Fills state.cache."""
         if not requests:
             return
+        self.batches.append(len(requests))
         if self.batched:
             questions = [DETECTION_QUESTION.format(st.target) for st, p in requests]
             if self.regions:       # the crop is cut on the GPU from the resident search image
@@ -306,42 +402,39 @@ class SearchController:
             if top_logit > st.confidence_high:
                 st.search_path[-1]["detection_result"] = final_bbox
                 if len(st.search_path) == 1:
-                    boxes, scores = ev.boxes, ev.scores
-                    if boxes.is_cuda:
-                        boxes, scores = boxes.cpu(), scores.cpu()
-                    av = boxes[scores.view(-1) > 0.5].view(-1, 4)
-                    av = av * torch.Tensor([[pw, ph, pw, ph]])
-                    av[:, :2] -= av[:, 2:] / 2
-                    st.all_valid_boxes = av
+                    st.all_valid_boxes = self._all_valid(ev, pw, ph)
                 return True
             st.search_path[-1]["temp_detection_result"] = (top_logit, final_bbox)
         if min(bb[2], bb[3]) <= st.smallest_size:
             return False
         h, w = bb[3], bb[2]
-        if ev.heat is None:
-            ev.heat = self.scorer.from_low_res(ev.low_res, h, w) if ev.low_res is not None else self.scorer.from_full_res(ev.full_map, h, w)
-        subs, _, _ = get_sub_patches(bb, *split_4subpatches(bb))
         idx = len(st.search_path) - 1
+        if ev.pyramid is not None:                 # record path: statistics and sums arrived with the batch
+            pyr = ev.pyramid
+            final_heat = LazyHeat(self.scorer, ev.low_res, h, w, ev.fetch_low_res)
+        else:
+            if ev.heat is None:
+                ev.heat = self.scorer.from_low_res(ev.low_res, h, w) if ev.low_res is not None else self.scorer.from_full_res(ev.full_map, h, w)
+            pyr = MapPyramid(self.scorer, ev.heat, bb)
+            final_heat = ev.heat
+        subs, _, _ = get_sub_patches(bb, *split_4subpatches(bb))
+        sub_keys = [tuple(int(v) for v in s) for s in subs]
 
-        def jobs_for(heat_of_cur):
-            jobs = []
+        def chain(pyr_of_cur):
+            out = []
             tmp = cur
             while True:
-                hm_t = heat_of_cur if tmp is cur else tmp["_heat"]
-                tb = tmp["bbox"]
-                rects = [[s[0] - tb[0], s[1] - tb[1], s[2], s[3]] for s in subs] + [[0, 0, tb[2], tb[3]]]
-                jobs.append((hm_t, rects, tmp["scale_level"]))
+                out.append((pyr_of_cur if tmp is cur else tmp["_pyr"], sub_keys + [tuple(int(v) for v in tmp["bbox"])], tmp["scale_level"]))
                 if tmp["parent_index"] == -1:
                     break
                 tmp = st.search_path[tmp["parent_index"]]
-            return jobs
+            return out
 
-        # optimistic strong-cue path: statistics and all rectangle sums come back in ONE device->host copy
-        jobs = jobs_for(ev.heat)
-        sums = self.scorer.rect_sums([(j[0], j[1]) for j in jobs])
-        score_max = float(ev.heat.host_stats()[0])
+        # optimistic strong-cue path: whatever is not already in a record comes back in ONE device->host copy
+        terms = chain(pyr)
+        fill_pyramids(self.scorer, [(t[0], t[1]) for t in terms])
+        score_max = float(pyr.stats[0])
         threshold = max(st.thr_min, st.thr * (st.thr_decay) ** (lvl - 1))
-        final_heat = ev.heat
         if not (score_max > threshold):
             # weak cue: ask the VSM where the object would be, then segment that region (visual_search.py:427-443)
             import copy
@@ -351,23 +444,39 @@ class SearchController:
             if phrase.endswith("."):
                 phrase = phrase[:-1]
             phrase = phrase.split(st.target)[-1]
-            chunks = self.extract_noun_chunks(phrase) if self.extract_noun_chunks is not None else []
+            chunks = self.extract_noun_chunks(phrase)
             phrase = chunks[0] if len(chunks) == 1 else "region {}".format(phrase)
             cue = self.vsm.inference(copy.deepcopy(patch_img), DETECTION_QUESTION.format(phrase), mode="segmentation")
             final_heat = cue if isinstance(cue, Heatmap) else self.scorer.from_full_res(cue, h, w)
             st.search_path[idx]["context_cue"] = vqa_results + "#" + phrase
-            jobs = jobs_for(final_heat)
-            sums = self.scorer.rect_sums([(j[0], j[1]) for j in jobs])
-        st.search_path[idx]["_heat"] = final_heat
+            pyr = MapPyramid(self.scorer, final_heat, bb)
+            terms = chain(pyr)
+            fill_pyramids(self.scorer, [(t[0], t[1]) for t in terms])
+        st.search_path[idx]["_pyr"] = pyr
         st.search_path[idx]["final_heatmap"] = final_heat      # lazily converts to the reference's [h,w,1] numpy array
         basic = [0] * len(subs)
-        for (hm_t, rects, level), sm in zip(jobs, sums):
-            tmp_scores = _sub_scores_from_sums(sm, len(subs))
+        for p_t, keys, level in terms:
+            tmp_scores = _sub_scores_from_sums([p_t.get(k) for k in keys], len(subs))
             basic = [basic[i] + tmp_scores[i] / (4 ** level) for i in range(len(subs))]
         for sp, sc in zip(subs, basic):
             info = dict(bbox=sp, scale_level=lvl + 1, score=sc, parent_index=idx)
             st.queue.put(Prioritize(-info["score"], info))
         return False
+
+    @staticmethod
+    def _all_valid(ev, pw, ph):
+        # visual_search.py:406-410 (only when the root itself succeeds)
+        if ev.valid_boxes is not None and ev.n_valid is not None:
+            av = ev.valid_boxes if ev.n_valid <= ev.valid_boxes.shape[0] else ev.fetch_valid()
+            av = av.clone().view(-1, 4)
+        else:
+            boxes, scores = ev.boxes, ev.scores
+            if boxes.is_cuda:
+                boxes, scores = boxes.cpu(), scores.cpu()
+            av = boxes[scores.view(-1) > 0.5].view(-1, 4)
+        av = av * torch.Tensor([[pw, ph, pw, ph]])
+        av[:, :2] -= av[:, 2:] / 2
+        return av
 
     def _advance(self, st: SearchState):
         """Commit as many nodes as the cache allows, in the reference's pop order."""
@@ -384,24 +493,49 @@ class SearchController:
             st.current = st.queue.get().item
             st.search_path.append(st.current)
 
+    def _select(self, active, limit):
+        """mandatory nodes first (the current node of every search that is not already in flight), then fill the batch with
+        speculation, round-robin over the active searches"""
+        reqs = [(st, st.current) for st in active if st._free(st.current)][:limit]
+        room = limit - len(reqs)
+        if room > 0 and active:
+            per = max(1, room // len(active)) + 1
+            extra = []
+            for st in active:
+                taken = [p for s2, p in reqs if s2 is st]
+                for p in st.wanted(per + len(taken)):
+                    if all(p is not t for t in taken):
+                        extra.append((st, p))
+            reqs += extra[:room]
+        return reqs
+
     def run(self, states):
+        from collections import deque
+        inflight = deque()
         while True:
             for st in states:
                 self._advance(st)
             active = [st for st in states if not st.done]
             if not active:
-                break
-            # mandatory nodes first, then fill the batch with speculation, round-robin over the active searches
-            reqs = [(st, st.current) for st in active]
-            room = self.batch_size - len(reqs)
-            if room > 0:
-                per = max(1, room // len(active)) + 1
-                extra = []
-                for st in active:
-                    for p in st.wanted(per)[1:]:
-                        extra.append((st, p))
-                reqs += extra[:room]
-            self._evaluate(reqs)
+                break                  # speculative batches still in flight are simply dropped
+            if not self.pipelined:
+                self._evaluate(self._select(active, self.batch_size))
+                continue
+            while len(inflight) < self.depth:
+                reqs = self._select(active, self.batch_size)
+                if not reqs:
+                    break
+                if not inflight and self.depth > 1 and len(reqs) >= 2 * self.split_min:
+                    # nothing queued behind this batch: cut it in two so that the second half runs on the GPU while the host
+                    # commits the first half and launches its successors
+                    half = (len(reqs) + 1) // 2
+                    inflight.append(self._launch(reqs[:half]))
+                    inflight.append(self._launch(reqs[half:]))
+                else:
+                    inflight.append(self._launch(reqs))
+            if not inflight:
+                raise RuntimeError("search controller stalled: active searches but nothing to evaluate")
+            self._collect(inflight.popleft())
         return [self._finish(st) for st in states]
 
     @staticmethod

@@ -162,11 +162,12 @@ class VQAEngine(LlamaClipCore):
         return x
 
     # ------------------------------------------------------------------ LM
-    def prefill_embeds(self, x):
-        """x [T,d] (consumed in place) -> residual stream after all layers; cache positions 0..T"""
+    def prefill_embeds(self, x, reserve=0):
+        """x [T,d] (consumed in place) -> residual stream after all layers; cache positions 0..T.  reserve: positions the
+        caller will append (the slot is sized for T + reserve; beyond the 2048 RoPE rows raises VsbError)"""
         T = x.shape[0]
-        assert T <= self.max_tokens, (T, self.max_tokens)
-        self._ensure_cache(1, self.max_tokens)
+        self._ensure_cache(1, self._capacity(T + reserve))
+        self._prefix_slots = 0
         self._llm_layers(x, 1, T, 0, self.max_tokens)
         self.kv_epoch = getattr(self, "kv_epoch", 0) + 1        # handles to an older prefix are stale from here on
         return x
@@ -175,6 +176,8 @@ class VQAEngine(LlamaClipCore):
         """run `tokens` (python list) on top of `past` cached positions -> logits fp32 [n, V] for every new position"""
         ids = torch.tensor(tokens, dtype=torch.int64, device=self.dev)
         x = ops.gather_rows(ids, self.w.embed)
+        if past + len(tokens) > self._cache_shape[2]:
+            self._ensure_cache(self._cache_shape[1], self._capacity(past + len(tokens) + 64), keep=True)
         self._llm_layers(x, 1, len(tokens), past, self.max_tokens)
         hn = ops.rmsnorm(x, self.w.final_norm, self.cfg.rms_eps)
         return ops.gemm(hn, self.w.lm_head, out_dtype=torch.float32)
@@ -190,14 +193,14 @@ class VQAEngine(LlamaClipCore):
         stop_ids: stop once the output ends with these ids; stop_fn(new_ids) -> bool: HF-style stopping criterion."""
         x = self.build_embeds(input_ids, image, object_crops, images_long, objects_long)
         T = x.shape[0]
-        self.prefill_embeds(x)
+        self.prefill_embeds(x, reserve=max(0, min(max_new_tokens, self.MAX_POSITIONS - T)))
         logits = self.last_logits(x)
         out = []
         past = T
         for _ in range(max_new_tokens):
             nxt = int(ops.argmax_rows(logits)[0][0])
             out.append(nxt)
-            if nxt == eos_token_id or (stop_ids and out[-len(stop_ids):] == list(stop_ids)) or past >= self.max_tokens - 1 or \
+            if nxt == eos_token_id or (stop_ids and out[-len(stop_ids):] == list(stop_ids)) or \
                     (stop_fn is not None and stop_fn(out)):
                 break
             logits = self.append_tokens([nxt], past)
@@ -205,7 +208,7 @@ class VQAEngine(LlamaClipCore):
         return out
 
     # ------------------------------------------------------------------ continuous-batched greedy decode
-    def prefill_ragged(self, xs):
+    def prefill_ragged(self, xs, reserve=0):
         """xs: list of [T_b, d] input embeddings (consumed).  Sequences are LEFT-padded in the shared cache: sequence b
         occupies cache rows [Tpad - T_b, Tpad) of batch slot b, so every sequence ends at the same row and one decode
         step is ONE set of kernels for the whole batch (each weight byte read once for B tokens).
@@ -213,8 +216,8 @@ class VQAEngine(LlamaClipCore):
         B = len(xs)
         lens = [int(x.shape[0]) for x in xs]
         Tpad = max(lens)
-        assert Tpad < self.max_tokens
-        self._ensure_cache(B, self.max_tokens)
+        self._ensure_cache(B, self._capacity(Tpad + reserve))
+        self._prefix_slots = 0
         Tm = self._cache_shape[2]
         last = []
         for b, x in enumerate(xs):
@@ -229,6 +232,8 @@ class VQAEngine(LlamaClipCore):
         B = len(lens)
         ids = torch.as_tensor(tokens, dtype=torch.int64, device=self.dev)
         x = ops.gather_rows(ids, self.w.embed)
+        if Tpad + step + 1 > self._cache_shape[2]:
+            self._ensure_cache(self._cache_shape[1], self._capacity(Tpad + step + 64), keep=True)
         positions = torch.tensor([n + step for n in lens], dtype=torch.int32, device=self.dev)
         k_start = torch.tensor([Tpad - n for n in lens], dtype=torch.int32, device=self.dev)
         self._llm_layers(x, B, 1, Tpad + step, self._cache_shape[2], positions=positions, k_start=k_start)
@@ -240,7 +245,8 @@ class VQAEngine(LlamaClipCore):
         Same per-sequence semantics as generate(); finished sequences idle (their slots keep stepping, results ignored).
         -> list of new-token lists"""
         xs = [self.build_embeds(ids, img, crops, il, ol) for ids, img, crops, il, ol in requests]
-        logits, Tpad, lens = self.prefill_ragged(xs)
+        longest = max(int(x.shape[0]) for x in xs)
+        logits, Tpad, lens = self.prefill_ragged(xs, reserve=max(0, min(max_new_tokens, self.MAX_POSITIONS - longest)))
         B = len(xs)
         outs = [[] for _ in range(B)]
         done = [False] * B
@@ -250,8 +256,7 @@ class VQAEngine(LlamaClipCore):
                 if done[b]:
                     continue
                 outs[b].append(int(nxt[b]))
-                if nxt[b] == eos_token_id or (stop_ids and outs[b][-len(stop_ids):] == list(stop_ids)) or \
-                        Tpad + step >= self.max_tokens - 1:
+                if nxt[b] == eos_token_id or (stop_ids and outs[b][-len(stop_ids):] == list(stop_ids)):
                     done[b] = True
             if all(done) or step == max_new_tokens - 1:
                 break

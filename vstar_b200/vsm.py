@@ -19,6 +19,7 @@ from . import ops
 from .config import VSMConfig, IMAGE_TOKEN_INDEX
 from .engine import VSMEngine, VSMWeights
 from .image import GpuImagePipeline
+from .records import pyramid_rects, record_floats
 from .visual_search import (DEFAULT_IM_END_TOKEN, DEFAULT_IM_START_TOKEN, DEFAULT_IMAGE_TOKEN, Heatmap, CudaScorer, _NodeEval)
 
 BF = torch.bfloat16
@@ -29,13 +30,22 @@ LLAVA_V1_SYSTEM = ("A chat between a curious human and an artificial intelligenc
                    "The assistant gives helpful, detailed, and polite answers to the human's questions.")
 
 
+LLAVA_LLAMA_2_SYSTEM = ("You are a helpful language and vision assistant. You are able to understand the visual content that the user "
+                        "provides, and assist the user with a variety of tasks using natural language.")
+
+
 def build_prompt(question, conv_type="llava_v1", use_mm_start_end=True):
     """visual_search.py:176-184 + conversation.py:355-365 (conv_llava_v1: SeparatorStyle.TWO, sep=' ', sep2='</s>')."""
     prompt = DEFAULT_IMAGE_TOKEN + "\n" + question
     if use_mm_start_end:
         prompt = prompt.replace(DEFAULT_IMAGE_TOKEN, DEFAULT_IM_START_TOKEN + DEFAULT_IMAGE_TOKEN + DEFAULT_IM_END_TOKEN)
+    if conv_type == "llava_llama_2":
+        # conversation.py conv_llava_llama_2 (SeparatorStyle.LLAMA_2, sep "<s>", sep2 "</s>"): the system prompt is wrapped in
+        # <<SYS>> and folded into the first [INST] block; the empty assistant turn adds nothing; leading "<s>" is stripped
+        sys_ = "<<SYS>>\n" + LLAVA_LLAMA_2_SYSTEM + "\n<</SYS>>\n\n"
+        return "[INST] " + sys_ + prompt + " [/INST]"
     if conv_type != "llava_v1":
-        raise NotImplementedError("only the llava_v1 template is on the hot path (visual_search.py:48 default)")
+        raise ValueError(f"unknown conv_type {conv_type!r} (visual_search.py:48: llava_v1 | llava_llama_2)")
     return LLAVA_V1_SYSTEM + " " + "USER" + ": " + prompt + " " + "ASSISTANT" + ":"
 
 
@@ -184,7 +194,9 @@ class VSM:
                 pfx = "model.vision_tower.vision_tower."
                 return clip(name[len(pfx):]) if name.startswith(pfx) else main(name)
 
-            engine = VSMEngine(VSMWeights(cfg, get))
+            # cache rows per crop: the tokenizer truncates text at model_max_length; the splice adds 255 rows; the cache grows
+            # on demand for generations beyond that (engine._ensure_cache)
+            engine = VSMEngine(VSMWeights(cfg, get), max_tokens=min(2048, int(args.model_max_length)))
             self.conv_type, self.use_mm_start_end = args.conv_type, args.use_mm_start_end
         else:
             self.conv_type, self.use_mm_start_end = "llava_v1", True
@@ -210,26 +222,39 @@ class VSM:
         # crops per engine call while search images are still being uploaded (see _run); 0 = never split
         self.upload_chunk = int(os.environ.get("VSB_UPLOAD_CHUNK", "16"))
         self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self._host_pool = {}
+        self._d2h_stream = None
 
     # ------------------------------------------------------------------ host prep
     def _staging(self, B):
+        """pinned staging buffers of the host-prep path, one set per batch size, guarded by the event of the last H2D copy out
+        of them (several prompt-length groups of the same size are launched back to back without a host sync)"""
         c = self.cfg
-        if B not in self._pinned:
-            self._pinned[B] = (torch.empty((B, 3, c.clip_image, c.clip_image), dtype=torch.float32).pin_memory(),
-                               torch.empty((B, 3, c.owl_image, c.owl_image), dtype=torch.float32).pin_memory())
-        return self._pinned[B]
+        slot = self._pinned.get(B)
+        if slot is None:
+            slot = [torch.empty((B, 3, c.clip_image, c.clip_image), dtype=torch.float32).pin_memory(),
+                    torch.empty((B, 3, c.owl_image, c.owl_image), dtype=torch.float32).pin_memory(), None]
+            self._pinned[B] = slot
+        if slot[2] is not None:
+            slot[2].synchronize()             # the copy queued by the previous user of this slot has read the buffer
+        return slot
 
     def _prep(self, images):
         """host path: PIL crops -> (clip [B,3,224,224], owl [B,3,768,768]) bf16 on the device"""
         c = self.cfg
         B = len(images)
-        pc, po = self._staging(B)
+        slot = self._staging(B)
+        pc, po = slot[0], slot[1]
         for i, im in enumerate(images):
             preprocess_clip_into(im, pc[i], c.clip_image)
             preprocess_owl_into(im, po[i], c.owl_image)
         self.h2d_bytes += pc.numel() * 4 + po.numel() * 4
-        ic = ops.cast_f32_bf16(pc.cuda(non_blocking=True))      # .bfloat16() of the reference (visual_search.py:189,194)
-        io = ops.cast_f32_bf16(po.cuda(non_blocking=True))
+        dc, do = pc.cuda(non_blocking=True), po.cuda(non_blocking=True)
+        slot[2] = torch.cuda.Event()
+        slot[2].record()
+        ic = ops.cast_f32_bf16(dc)      # .bfloat16() of the reference (visual_search.py:189,194)
+        io = ops.cast_f32_bf16(do)
         return ic, io
 
     def resident(self, pil_img):
@@ -269,16 +294,37 @@ class VSM:
         return tokenizer_image_token(prompt, self.vsm_tokenizer)
 
     # ------------------------------------------------------------------ engine calls
-    def _run(self, regions, questions, mode):
-        """regions: list of (source PIL image, bbox) -> list (per crop) of dicts with device tensors"""
+    def _host_buffer(self, shape, dtype):
+        """pinned host buffers for the per-batch D2H copies, recycled (page-locking per batch costs more than the copy)"""
+        n = 1
+        for v in shape:
+            n *= int(v)
+        key = (dtype, max(1024, 1 << (max(1, n) - 1).bit_length()))
+        pool = self._host_pool.setdefault(key, [])
+        buf = pool.pop() if pool else torch.empty((key[1],), dtype=dtype).pin_memory()
+        return buf, key
+
+    def _launch(self, regions, questions, mode, smallest=None, rec_len=None):
+        """Queue the evaluation of a batch on the GPU and return at once (nothing here waits for the device).
+        regions: list of (source PIL image, bbox).  smallest: per-region smallest_size => crop RECORDS are produced on the
+        device (records.py) and copied to pinned host memory on a side stream; None => per-crop tensors only."""
         import time
         t0 = time.perf_counter()
+        dev = self.engine.dev
+        n = len(regions)
         ids_list = [self._ids(q) for q in questions]
         groups = {}
         for i, ids in enumerate(ids_list):
             groups.setdefault((len(ids), ids.index(IMAGE_TOKEN_INDEX)), []).append(i)
-        results = [None] * len(regions)
-        pending = []
+        pend = dict(n=n, mode=mode, regions=regions, smallest=smallest, chunks=[], rec=None, rects=None, low=[None] * n,
+                    det=[None] * n)
+        rec = None
+        if smallest is not None:
+            rects = [pyramid_rects(b, ss) for (_, b), ss in zip(regions, smallest)]
+            R = record_floats(max(len(r) for r in rects))
+            rec = torch.zeros((n, max(R, rec_len or 0)), dtype=torch.float32, device=dev)
+            pend["rec"], pend["rects"] = rec, rects
+        heat_jobs = []
         for key, members in groups.items():
             # Search images that are not resident yet cost ~1.5 ms of host time each (PIL -> pinned staging -> H2D).  Such a
             # group is cut into chunks whose engine work is launched WITHOUT waiting for the GPU (defer=True), so the host
@@ -293,19 +339,127 @@ class VSM:
                 prompt = torch.tensor([ids_list[i] for i in chunk], dtype=torch.int64)
                 out = self.engine.inference(io, ic, prompt, self.draft_ids, eos_token_id=self.eos, mode=mode,
                                             forced_ids=self.forced_answer_ids, defer=True)
-                pending.append((chunk, out, io, ic, prompt))
+                if rec is not None:
+                    heat_jobs += self._pack_chunk(out, chunk, pend)
+                pend["chunks"].append([chunk, out, io, ic, prompt, None])
                 t0 = time.perf_counter()
                 self.timers["engine"] += t0 - t1
-        for chunk, out, io, ic, prompt in pending:
-            self.engine.finish(out)
-            bad = [j for j, ok in enumerate(out["verified"]) if not ok]
+        if heat_jobs:
+            c = self.cfg
+            ops.heat_pyramids(heat_jobs, rec, 4 * c.owl_grid, 4 * c.owl_grid)
+        # device -> host on a side stream: finish() waits for THIS batch only, not for whatever was queued behind it
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        if self._d2h_stream is None:
+            self._d2h_stream = torch.cuda.Stream(device=dev)
+        keys = []
+        with torch.cuda.stream(self._d2h_stream):
+            self._d2h_stream.wait_event(ready)
+            if rec is not None:
+                buf, key = self._host_buffer(rec.shape, torch.float32)
+                keys.append((key, buf))
+                pend["rec_host"] = buf[:rec.numel()].view(rec.shape)
+                pend["rec_host"].copy_(rec, non_blocking=True)
+                rec.record_stream(self._d2h_stream)
+                self.d2h_bytes += rec.numel() * 4
+            for ch in pend["chunks"]:
+                am = ch[1].get("_am")
+                if am is not None:
+                    buf, key = self._host_buffer(am.shape, am.dtype)
+                    keys.append((key, buf))
+                    ch[5] = buf[:am.numel()].view(am.shape)
+                    ch[5].copy_(am, non_blocking=True)
+                    am.record_stream(self._d2h_stream)
+                    self.d2h_bytes += am.numel() * am.element_size()
+            done = torch.cuda.Event()
+            done.record(self._d2h_stream)
+        pend["done"], pend["host_keys"] = done, keys
+        self.timers["engine"] += time.perf_counter() - t0
+        return pend
+
+    def _pack_chunk(self, out, chunk, pend):
+        """detections of one engine call -> record rows (device); returns the heat-map jobs of its expandable crops"""
+        rec, rects = pend["rec"], pend["rects"]
+        col = out["crop_of_loc"]
+        B = len(chunk)
+        scores, boxes, low = out["scores"], out["pred_boxes"], out["low_res_masks"]
+        if col == list(range(B)):
+            first = last = list(range(B))
+        else:                                   # several [LOC] per answer: pred_boxes[0] / pred_mask[-1] (visual_search.py:208-211)
+            first = [col.index(j) for j in range(B)]
+            last = [len(col) - 1 - col[::-1].index(j) for j in range(B)]
+            idx = torch.tensor(first, device=scores.device)
+            scores, boxes = scores.index_select(0, idx).contiguous(), boxes.index_select(0, idx).contiguous()
+        if chunk == list(range(chunk[0], chunk[0] + B)):
+            ops.pack_detections(scores.contiguous(), boxes.contiguous(), rec, row0=chunk[0])
+        else:
+            tmp = torch.zeros((B, rec.shape[1]), dtype=torch.float32, device=rec.device)
+            ops.pack_detections(scores.contiguous(), boxes.contiguous(), tmp)
+            rec.index_copy_(0, torch.tensor(chunk, device=rec.device), tmp)
+        jobs = []
+        for j, i in enumerate(chunk):
+            pend["low"][i] = low[last[j]]
+            pend["det"][i] = (scores[j], boxes[j])
+            if rects[i]:
+                bb = pend["regions"][i][1]
+                x0, y0 = int(bb[0]), int(bb[1])
+                jobs.append((low[last[j]], int(bb[3]), int(bb[2]), [(r[0] - x0, r[1] - y0, r[2], r[3]) for r in rects[i]], i))
+        return jobs
+
+    def _finish(self, pend):
+        """wait for the batch's device->host copies, resolve the draft verification, return per-crop results:
+        record mode -> list of _NodeEval; otherwise list of dicts with device tensors"""
+        import time
+        t0 = time.perf_counter()
+        pend["done"].synchronize()
+        mode, n = pend["mode"], pend["n"]
+        results = [None] * n
+        redo = []
+        for chunk, out, io, ic, prompt, am_host in pend["chunks"]:
+            self.engine.finish(out, am_host)
             for j, i in enumerate(chunk):
-                if j in bad:
-                    results[i] = self._exact_single(io[j:j + 1], ic[j:j + 1], prompt[j:j + 1], mode)
+                if out["verified"][j]:
+                    results[i] = self._slice(out, j, mode) if pend["rec"] is None else True
                 else:
-                    results[i] = self._slice(out, j, mode)
+                    redo.append((i, io[j:j + 1], ic[j:j + 1], prompt[j:j + 1]))
+        rows = pend["rec_host"].numpy() if pend["rec"] is not None else None
+        for i, io1, ic1, prompt1 in redo:
+            r = self._exact_single(io1, ic1, prompt1, mode)          # exact greedy decode of this crop (synchronous, rare)
+            if rows is None:
+                results[i] = r
+                continue
+            rec1 = torch.zeros((1, rows.shape[1]), dtype=torch.float32, device=self.engine.dev)
+            ops.pack_detections(r["scores"].view(1, -1).contiguous(), r["boxes"].view(1, -1, 4).contiguous(), rec1)
+            if pend["rects"][i]:
+                bb = pend["regions"][i][1]
+                x0, y0 = int(bb[0]), int(bb[1])
+                ops.heat_pyramids([(r["low_res"].contiguous(), int(bb[3]), int(bb[2]),
+                                    [(q[0] - x0, q[1] - y0, q[2], q[3]) for q in pend["rects"][i]], 0)], rec1,
+                                  r["low_res"].shape[-2], r["low_res"].shape[-1])
+            rows[i] = rec1.cpu().numpy()[0]
+            pend["low"][i], pend["det"][i] = r["low_res"], (r["scores"].view(-1), r["boxes"].view(-1, 4))
+            results[i] = True
+        if rows is not None:
+            for i in range(n):
+                ev = _NodeEval.from_record(rows[i], pend["regions"][i][1], pend["smallest"][i])
+                ev.low_res = pend["low"][i]
+                ev.scores, ev.boxes = pend["det"][i]
+
+                def fetch_valid(sb=pend["det"][i]):
+                    return sb[1][sb[0].view(-1) > 0.5].view(-1, 4).cpu()
+
+                ev.fetch_valid = fetch_valid
+                results[i] = ev
+            rows = None
+        for key, buf in pend["host_keys"]:
+            self._host_pool.setdefault(key, []).append(buf)
         self.timers["engine"] += time.perf_counter() - t0
         return results
+
+    def _run(self, regions, questions, mode):
+        """regions: list of (source PIL image, bbox) -> list (per crop) of dicts with device tensors"""
+        return self._finish(self._launch(regions, questions, mode))
 
     def _exact_single(self, io, ic, prompt, mode):
         """draft mismatch: exact greedy decode on the KV cache, then one teacher-forced pass over the emitted ids
@@ -358,24 +512,24 @@ class VSM:
         return self.detect_regions([(im, [0, 0, im.width, im.height]) for im in images], questions)
 
     @torch.inference_mode()
-    def detect_regions(self, regions, questions):
-        """Batched detection-mode evaluation for the search controller: regions = [(search image, bbox)] -> [_NodeEval]."""
-        rs = self._run(regions, questions, "detection")
-        sc = torch.stack([r["scores"] for r in rs])                          # [n, P]
-        idx, val = ops.argmax_rows(sc.contiguous())
-        bx = torch.stack([r["boxes"] for r in rs])                           # [n, P, 4]
-        top = bx[torch.arange(len(rs), device=bx.device), idx.long()]
-        host = torch.cat([val.view(-1, 1), top], dim=1).cpu()                # one D2H for the whole batch
-        out = []
-        for i, r in enumerate(rs):
-            ev = _NodeEval()
-            ev.n_logits = r["scores"].numel()
-            ev.top_logit = float(host[i, 0])
-            ev.top_box = host[i, 1:].clone()
-            ev.boxes, ev.scores = r["boxes"], r["scores"].view(-1, 1)
-            ev.low_res = r["low_res"]
-            out.append(ev)
-        return out
+    def detect_regions_launch(self, regions, questions, smallest_sizes, rec_len=None):
+        """Asynchronous batched detection-mode evaluation for the search controller: regions = [(search image, bbox)].
+        smallest_sizes[i] = the search's smallest_size (decides whether crop i will ever be split, i.e. needs the heat-map
+        part of its record).  rec_len: record length in floats when the caller needs a common one (sharded frontier: the
+        all-gather wants the same record size on every rank).  Returns a handle for detect_regions_finish."""
+        return self._launch(regions, questions, "detection", smallest=list(smallest_sizes), rec_len=rec_len)
+
+    @torch.inference_mode()
+    def detect_regions_finish(self, handle):
+        """-> [_NodeEval] built from the batch's crop records (one D2H per batch, issued at launch on a side stream)"""
+        return self._finish(handle)
+
+    def detect_regions(self, regions, questions, smallest_sizes=None):
+        """synchronous form.  Without smallest_sizes every crop gets the heat-map statistics and the sums of its four children
+        (enough for one expansion; deeper levels need the search's smallest_size)."""
+        if smallest_sizes is None:
+            smallest_sizes = [max(1, min(int(b[2]), int(b[3])) // 2) for _, b in regions]
+        return self.detect_regions_finish(self.detect_regions_launch(regions, questions, smallest_sizes))
 
 
 # ----------------------------------------------------------------------------------------------------------------
