@@ -142,6 +142,56 @@ def option_losses(sd, cfg, question_ids, options_ids, image, object_crops=None, 
     return losses, int(losses.argmin())
 
 
+def llama_forward_cached(sd, cfg, embeds, past=None):
+    """HF LlamaModel with `use_cache=True` (as driven by vstar_bench_eval.py:127-152): `embeds` [1,Tn,d] are appended after
+    the `past` keys/values (list of (k, v) per layer, [1,H,Tp,hd]); -> (final-normed states of the new rows, new past).
+    Same arithmetic as vsm_oracle.llama_forward, restricted to the new rows."""
+    B, Tn, d = embeds.shape
+    H, hd = cfg.n_heads, cfg.head_dim
+    Tp = 0 if past is None else past[0][0].shape[2]
+    cos, sin = O.rope_cos_sin(Tn, hd, cfg.rope_theta, embeds.dtype, start=Tp)
+    mask = torch.full((Tn, Tp + Tn), float("-inf"), dtype=embeds.dtype).triu(Tp + 1)
+    x = embeds
+    new_past = []
+    for i in range(cfg.n_layers):
+        p = f"model.layers.{i}."
+        h = O.rmsnorm(x, sd[p + "input_layernorm.weight"], cfg.rms_eps)
+        q = F.linear(h, sd[p + "self_attn.q_proj.weight"]).view(B, Tn, H, hd).transpose(1, 2)
+        k = F.linear(h, sd[p + "self_attn.k_proj.weight"]).view(B, Tn, H, hd).transpose(1, 2)
+        v = F.linear(h, sd[p + "self_attn.v_proj.weight"]).view(B, Tn, H, hd).transpose(1, 2)
+        q = q * cos + O.rotate_half(q) * sin
+        k = k * cos + O.rotate_half(k) * sin
+        if past is not None:
+            k, v = torch.cat([past[i][0], k], dim=2), torch.cat([past[i][1], v], dim=2)
+        new_past.append((k, v))
+        att = torch.matmul(q, k.transpose(2, 3)) * (hd ** -0.5) + mask
+        att = torch.softmax(att, dim=-1, dtype=torch.float32).to(q.dtype)
+        o = torch.matmul(att, v).transpose(1, 2).reshape(B, Tn, d)
+        x = x + F.linear(o, sd[p + "self_attn.o_proj.weight"])
+        h = O.rmsnorm(x, sd[p + "post_attention_layernorm.weight"], cfg.rms_eps)
+        g = F.silu(F.linear(h, sd[p + "mlp.gate_proj.weight"])) * F.linear(h, sd[p + "mlp.up_proj.weight"])
+        x = x + F.linear(g, sd[p + "mlp.down_proj.weight"])
+    return O.rmsnorm(x, sd["model.norm.weight"], cfg.rms_eps), new_past
+
+
+def option_losses_cached(sd, cfg, question_ids, options_ids, image, object_crops=None, images_long=None, objects_long=None):
+    """multiple_choices_inference AS WRITTEN (vstar_bench_eval.py:127-163): ONE forward over the question (logits for every
+    position, `use_cache=True`), then each option is appended on top of the question's past_key_values.  Same numbers as
+    option_losses (which recomputes the prefix per option); this is the variant whose COST equals the reference's."""
+    emb = sd["model.embed_tokens.weight"]
+    q_embeds = build_embeds(sd, cfg, question_ids, image, object_crops, images_long, objects_long)
+    hq, past = llama_forward_cached(sd, cfg, q_embeds)
+    q_logits = F.linear(hq, sd["lm_head.weight"])                       # the reference computes them for all T rows
+    losses = []
+    for opt in options_ids:
+        ho, _ = llama_forward_cached(sd, cfg, emb[opt].unsqueeze(0), past)
+        lo = F.linear(ho, sd["lm_head.weight"])
+        lg = torch.cat([q_logits[0, -1:], lo[0, :-1]], dim=0)            # vstar_bench_eval.py:153
+        losses.append(F.cross_entropy(lg.float(), opt))
+    losses = torch.stack(losses)
+    return losses, int(losses.argmin())
+
+
 # ---------------------------------------------------------------- host helpers (vstar_bench_eval.py:25-76)
 def expand2square_center(pil_img, background_color):
     from PIL import Image

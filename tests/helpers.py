@@ -19,7 +19,10 @@ class NumpyHeat:
         return self._n
 
     def __array__(self, dtype=None, copy=None):
-        return self.norm().reshape(self.h, self.w, 1)
+        # what the reference stores in search_path[i]['final_heatmap']: normalize_score in fp32, [h,w,1] (visual_search.py:268-275, :448)
+        mx, mn = self.arr.max(), self.arr.min()
+        a = ((self.arr - mn) / (mx - mn) if mx != mn else self.arr * 0).astype(np.float32).reshape(self.h, self.w, 1)
+        return a.astype(dtype) if dtype is not None else a
 
 
 class NumpyScorer:

@@ -185,7 +185,30 @@ def check_noun_chunks():
         assert NC.filter_chunk_list(chunks) == ref.filter_chunk_list(chunks)
 
 
-@pytest.mark.parametrize("name", ["check_noun_chunks", "check_split_and_sub_patches", "check_refine_bbox_and_iou", "check_prioritize_pop_order_with_ties",
+def check_visualisation_files():
+    """visualize=True: the files visualize_search_path writes (visual_search.py:339-376) from the reference and from the product,
+    on the same stub search: same file names, byte-identical JPEGs and context_cue.txt"""
+    import tempfile
+    ref = load_reference()
+    from tests.helpers import FakeNLP, NumpyScorer, StubVSM, synth_image
+    from vstar_b200 import noun_chunks
+    from vstar_b200 import visual_search as VS
+    ref.nlp = FakeNLP()
+    noun_chunks.set_nlp(FakeNLP())
+    for seed, w, h, smallest, hot, kw in ((29, 640, 480, 224, None, dict(confidence_high=2.0, target_cue_threshold=9.5, target_cue_threshold_minimum=9.5)),
+                                          (25, 700, 600, 224, "small", dict())):
+        img = synth_image(seed, w, h)
+        with tempfile.TemporaryDirectory() as a, tempfile.TemporaryDirectory() as b:
+            ra = ref.visual_search(StubVSM(hot), img, "mug", [30, 40, 50, 60], smallest, visualize=True, save_path=a, **kw)
+            rb = VS.visual_search(StubVSM(hot), img, "mug", [30, 40, 50, 60], smallest, visualize=True, save_path=b, scorer=NumpyScorer(), **kw)
+            assert ra[1] == rb[1] and ra[2] == rb[2]
+            fa, fb = sorted(os.listdir(a)), sorted(os.listdir(b))
+            assert fa == fb and "whole_image.jpg" in fa and "context_cue.txt" in fa and any(f.endswith("_heatmap.jpg") for f in fa), (fa, fb)
+            for f in fa:
+                assert open(os.path.join(a, f), "rb").read() == open(os.path.join(b, f), "rb").read(), f
+
+
+@pytest.mark.parametrize("name", ["check_visualisation_files", "check_noun_chunks", "check_split_and_sub_patches", "check_refine_bbox_and_iou", "check_prioritize_pop_order_with_ties",
                                   "check_prompts_and_token_splicing", "check_padding_and_patch_geometry"])
 def test_against_live_reference(name):
     isolated(name)

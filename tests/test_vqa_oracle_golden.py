@@ -33,6 +33,9 @@ def test_vqa_oracle_golden(sub):
     losses, choice = V.option_losses(sd, cfg, q, opts, image, crops, il, ol)
     assert torch.allclose(losses, torch.from_numpy(g["option_losses"]), rtol=1e-4, atol=1e-4)
     assert choice == int(np.argmin(g["option_losses"]))
+    # the as-written variant (question prefilled once, options appended on its past_key_values) gives the same numbers
+    losses_c, choice_c = V.option_losses_cached(sd, cfg, q, opts, image, crops, il, ol)
+    assert torch.allclose(losses_c, torch.from_numpy(g["option_losses"]), rtol=1e-4, atol=1e-4) and choice_c == choice
     assert V.free_form_generate(sd, cfg, q, image, crops, il, ol, max_new_tokens=4, eos_token_id=-1) == g["gen"].tolist()
 
 

@@ -135,35 +135,27 @@ __global__ void mask_dot_kernel(const bf16* __restrict__ up, const bf16* __restr
 //   (/root/reference/VisualSearch/model/VSM.py:534-537; /root/reference/visual_search.py:223-224)
 // Same arithmetic order as ATen's upsample_bilinear2d (fp32 accscalar).  Also emits per-block partial
 // (max, min, sum) so the search controller never has to re-read the H x W map for its statistics.
-// One pixel of F.interpolate(low, (h, w), mode="bilinear", align_corners=False) (+ clamp): written with explicit
-// round-to-nearest ops (no FMA contraction) so that EVERY kernel that evaluates the map (materialising heatmap_kernel, the
-// fused statistics / rectangle-sum kernels of the crop records) produces bit-identical values.
+// One pixel of F.interpolate(low, (h, w), mode="bilinear", align_corners=False) (+ clamp), same expression as ATen's
+// upsample_bilinear2d (fp32 accscalar; nvcc contracts it into FMAs as it does for ATen).  Deliberately NOT inlined: every
+// kernel that evaluates the map (materialising heatmap_kernel, the fused statistics / rectangle-sum kernels of the crop
+// records) calls this one compiled body, so they all produce bit-identical values.
 struct HeatGeom {
   const float* low;
   int LH, LW;
   float rh, rw;
   int do_clamp;
 };
-__device__ __forceinline__ void heat_src(float scale, int o, int L, int& i0, int& i1, float& l, float& hcoef) {
-  float s = __fadd_rn(__fmul_rn(scale, (float)o + 0.5f), -0.5f);
-  if (s < 0.f) s = 0.f;
-  i0 = (int)s;
-  i1 = i0 + (i0 < L - 1 ? 1 : 0);
-  l = __fadd_rn(s, -(float)i0);
-  hcoef = __fadd_rn(1.f, -l);
-}
-__device__ __forceinline__ float heat_px(const HeatGeom& g, int y0, int y1, float ly, float hy, int ox) {
-  int x0, x1;
-  float lx, hx;
-  heat_src(g.rw, ox, g.LW, x0, x1, lx, hx);
-  const float* r0 = g.low + y0 * g.LW;
-  const float* r1 = g.low + y1 * g.LW;
-  const float top = __fadd_rn(__fmul_rn(hx, __ldg(r0 + x0)), __fmul_rn(lx, __ldg(r0 + x1)));
-  const float bot = __fadd_rn(__fmul_rn(hx, __ldg(r1 + x0)), __fmul_rn(lx, __ldg(r1 + x1)));
-  float v = __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
-  if (g.do_clamp) v = fmaxf(v, 0.f);
+__device__ __noinline__ float heat_px(const float* __restrict__ low, int LH, int LW, float rh, float rw, int do_clamp, int oy, int ox) {
+  float sy = rh * (oy + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
+  float sx = rw * (ox + 0.5f) - 0.5f; if (sx < 0.f) sx = 0.f;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + (y0 < LH - 1 ? 1 : 0), x1 = x0 + (x0 < LW - 1 ? 1 : 0);
+  const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
+  float v = hy * (hx * low[y0 * LW + x0] + lx * low[y0 * LW + x1]) + ly * (hx * low[y1 * LW + x0] + lx * low[y1 * LW + x1]);
+  if (do_clamp) v = fmaxf(v, 0.f);
   return v;
 }
+__device__ __forceinline__ float heat_px(const HeatGeom& g, int oy, int ox) { return heat_px(g.low, g.LH, g.LW, g.rh, g.rw, g.do_clamp, oy, ox); }
 
 __global__ void __launch_bounds__(256) heatmap_kernel(const float* __restrict__ low, int LH, int LW, float* __restrict__ out, int h,
                                                       int w, int do_clamp, float* __restrict__ partial) {
@@ -173,10 +165,7 @@ __global__ void __launch_bounds__(256) heatmap_kernel(const float* __restrict__ 
   float mx = -INFINITY, mn = INFINITY, sm = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int oy = i / w, ox = i - (long long)oy * w;
-    int y0, y1;
-    float ly, hy;
-    heat_src(g.rh, oy, LH, y0, y1, ly, hy);
-    const float v = heat_px(g, y0, y1, ly, hy, ox);
+    const float v = heat_px(g, oy, ox);
     out[i] = v;
     mx = fmaxf(mx, v); mn = fminf(mn, v); sm += v;
   }
@@ -357,11 +346,8 @@ __global__ void __launch_bounds__(256) heat_stats_kernel(const int* __restrict__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float mx = -INFINITY, mn = INFINITY, sm = 0.f;
   for (int oy = ya + warp; oy < yb; oy += 8) {
-    int y0, y1;
-    float ly, hy;
-    heat_src(g.rh, oy, LH, y0, y1, ly, hy);
     for (int ox = lane; ox < jb.w; ox += 32) {
-      const float v = heat_px(g, y0, y1, ly, hy, ox);
+      const float v = heat_px(g, oy, ox);
       mx = fmaxf(mx, v); mn = fminf(mn, v); sm += v;
     }
   }
@@ -420,13 +406,10 @@ __global__ void __launch_bounds__(256) heat_rects_kernel(const int* __restrict__
     const int yb = min(y1, ya + per);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int yy = ya + warp; yy < yb; yy += 8) {
-      int sy0, sy1;
-      float ly, hy;
-      heat_src(g.rh, yy, LH, sy0, sy1, ly, hy);
       float acc = 0.f;
       int k = 0;
       for (int xx = x0 + lane; xx < x1; xx += 32) {
-        acc = __fadd_rn(acc, norm_px(heat_px(g, sy0, sy1, ly, hy, xx), sub, den));
+        acc = __fadd_rn(acc, norm_px(heat_px(g, yy, xx), sub, den));
         if (++k == 64) { dacc += acc; acc = 0.f; k = 0; }
       }
       dacc += acc;

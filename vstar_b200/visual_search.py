@@ -561,22 +561,26 @@ class SearchController:
 def visual_search(vsm, image, target_object_name, target_bbox, smallest_size, confidence_high=0.5, confidence_low=0.3,
                   target_cue_threshold=6.0, target_cue_threshold_decay=0.7, target_cue_threshold_minimum=3.0,
                   visualize=False, save_path=None, scorer=None, batch_size=None, extract_noun_chunks=None,
-                  return_state=False):
+                  return_state=False, depth=2):
     """Same contract as the reference's visual_search() (visual_search.py:484-516)."""
     if visualize:
-        raise NotImplementedError("visualisation (cv2 overlays, visual_search.py:339-376) is outside the hot path")
+        assert save_path is not None
     st = SearchState(image, target_object_name, smallest_size, confidence_high, confidence_low, target_cue_threshold,
                      target_cue_threshold_decay, target_cue_threshold_minimum)
     if batch_size is None:
         batch_size = getattr(vsm, "frontier_batch", 1)
-    ctl = SearchController(vsm, scorer, batch_size, extract_noun_chunks)
+    ctl = SearchController(vsm, scorer, batch_size, extract_noun_chunks, depth=depth)
     res = ctl.run([st])[0]
+    if visualize:                          # visual_search.py:512-514
+        from .visualize import visualize_search_path
+        vis_len = res[1] if res[2] else len(st.search_path)
+        visualize_search_path(image, st.search_path, vis_len, target_bbox, target_object_name, save_path)
     return res + (st,) if return_state else res
 
 
-def visual_search_many(vsm, jobs, batch_size=8, scorer=None, extract_noun_chunks=None, **kw):
+def visual_search_many(vsm, jobs, batch_size=8, scorer=None, extract_noun_chunks=None, depth=2, **kw):
     """Run several independent searches in lock-step so their frontiers share GPU batches.
-    jobs: list of (image, target_object_name, smallest_size).  Returns (results, states)."""
+    jobs: list of (image, target_object_name, smallest_size).  depth: frontier batches in flight.  Returns (results, states)."""
     states = [SearchState(img, name, ss, **kw) for img, name, ss in jobs]
-    ctl = SearchController(vsm, scorer, batch_size, extract_noun_chunks)
+    ctl = SearchController(vsm, scorer, batch_size, extract_noun_chunks, depth=depth)
     return ctl.run(states), states

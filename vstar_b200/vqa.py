@@ -393,7 +393,7 @@ def load_pretrained_model(model_path, model_base=None, model_name=None, load_8bi
     from .vsm import config_from_hf, open_checkpoint
     tokenizer = AutoTokenizer.from_pretrained(model_path, use_fast=False)
     cfg = config_from_hf(model_path)
-    engine = VQAEngine(VQAWeights(cfg, open_checkpoint(model_path), device=device))
+    engine = VQAEngine(VQAWeights(cfg, open_checkpoint(model_path, device=device), device=device))
     return tokenizer, LlavaSearchModel(engine, getattr(tokenizer, "eos_token_id", 2)), _Proc(), 2048
 
 

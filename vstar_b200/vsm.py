@@ -143,24 +143,7 @@ def preprocess_owl_into(pil_img, dst, size=768):
 # ----------------------------------------------------------------------------------------------------------------
 # checkpoint reader (HF sharded safetensors / .bin with the reference key layout)
 # ----------------------------------------------------------------------------------------------------------------
-def open_checkpoint(path):
-    """-> callable name -> tensor, over *.safetensors or pytorch_model*.bin shards in `path`."""
-    files = sorted(glob.glob(os.path.join(path, "*.safetensors")))
-    if files:
-        from safetensors import safe_open
-        index = {}
-        handles = [safe_open(f, framework="pt", device="cpu") for f in files]
-        for h in handles:
-            for k in h.keys():
-                index[k] = h
-        return lambda name: index[name].get_tensor(name)
-    files = sorted(glob.glob(os.path.join(path, "pytorch_model*.bin")))
-    if not files:
-        raise FileNotFoundError(f"no *.safetensors / pytorch_model*.bin under {path}")
-    merged = {}
-    for f in files:
-        merged.update(torch.load(f, map_location="cpu", weights_only=True))
-    return lambda name: merged[name]
+from .checkpoint import open_checkpoint  # noqa: E402,F401  (safetensors -> GPU streaming reader / mmap'd .bin shards)
 
 
 def config_from_hf(path) -> VSMConfig:
@@ -187,8 +170,8 @@ class VSM:
             tokenizer.pad_token = tokenizer.unk_token
             cfg = config_from_hf(args.version)
             cfg.loc_token_idx = tokenizer("[LOC]", add_special_tokens=False).input_ids[0]
-            main = open_checkpoint(args.version)
-            clip = open_checkpoint(args.vision_tower)        # CLIP weights are not in the VSM checkpoint (merge...py:146-149)
+            main = open_checkpoint(args.version, device="cuda")
+            clip = open_checkpoint(args.vision_tower, device="cuda")     # CLIP weights are not in the VSM checkpoint (merge...py:146-149)
 
             def get(name):
                 pfx = "model.vision_tower.vision_tower."
@@ -575,14 +558,14 @@ class VSMForCausalLM:
         cfg = config_from_hf(version)
         if loc_token_idx is not None:
             cfg.loc_token_idx = int(loc_token_idx)
-        main = open_checkpoint(version)
-        clip = open_checkpoint(vision_tower)
+        device = "cuda" if device_map in ("cuda", "auto") else device_map
+        main = open_checkpoint(version, device=device)
+        clip = open_checkpoint(vision_tower, device=device)
 
         def get(name):
             pfx = "model.vision_tower.vision_tower."
             return clip(name[len(pfx):]) if name.startswith(pfx) else main(name)
 
-        device = "cuda" if device_map in ("cuda", "auto") else device_map
         return cls(VSMEngine(VSMWeights(cfg, get, device=device)), vision_tower)
 
     # -- HF-style accessors used by the reference wrapper
