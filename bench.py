@@ -8,8 +8,8 @@
 Headline workload = BASELINE.json configs[2]: 2048x2048 synthetic images, smallest_size 512 => every
 search evaluates 1 + 4 + 16 = 21 crops; 8 searches run in lock-step, each feeding up to 8 frontier crops into a batch of <= 64
 crops; after the searches every search's question is answered by ONE SEAL-VQA `multiple_choices_inference` (4 options, 2 object
-crops spliced in as <object> features: vstar_bench_eval.py:116-165, :226-257).  A "step" = those 8 searches + 8 option
-scorings; crops/s = 168 / step time.  Every crop evaluation = CLIP ViT-L/14 -> projector -> Vicuna-7B-shaped prefill (draft
+crops spliced in as <object> features: vstar_bench_eval.py:116-165, :226-257; the 8 scorings of a step run as one batch).
+A "step" = those 8 searches + 8 option scorings; crops/s = 168 / step time.  Every crop evaluation = CLIP ViT-L/14 -> projector -> Vicuna-7B-shaped prefill (draft
 -verified answer) -> OWL-ViT-B/16 -> SAM prompt/mask decoder -> OWL heads -> crop record (heat-map statistics + rectangle sums);
 random-init weights of the reference architecture, synthetic images.
 
@@ -425,7 +425,7 @@ def run_b200(args):
 
         def vqa_public(results):
             # the call a user makes after the searches (vstar_bench_eval.py:226-257): PIL crops, host CLIP preprocessing, H2D
-            return [seal.choose_option(vqa, im, QUESTION, OPTIONS, list(TARGETS), search_result_of(r)) for im, r in zip(images, results)]
+            return seal.choose_options(vqa, [(im, QUESTION, OPTIONS, list(TARGETS), search_result_of(r)) for im, r in zip(images, results)])
 
         def stage_vqa(results):
             """device-resident inputs of the same option scorings (built once from a warm-up run; searches are deterministic)"""
@@ -441,7 +441,7 @@ def run_b200(args):
                 q_ids = tokenizer_image_object_token(build_prompt_v1(qs), vqa.tokenizer)
                 opt_ids = [tokenizer_image_object_token(build_prompt_v1(qs, o), vqa.tokenizer)[len(q_ids):] for o in OPTIONS]
                 img_d, crops_d = vqa._pixels(padded, crops)
-                staged.append((q_ids, opt_ids, img_d, crops_d))
+                staged.append((q_ids, opt_ids, img_d, crops_d, [False], [True, True]))
             return staged
 
         def step(resident):
@@ -453,7 +453,7 @@ def run_b200(args):
                 if resident:
                     if state["vqa_resident"] is None:
                         state["vqa_resident"] = stage_vqa(results)
-                    choices = [vqa.engine.option_losses(q, o, i, c, [False], [True, True])[1] for q, o, i, c in state["vqa_resident"]]
+                    choices = [c for _, c in vqa.engine.option_losses_batch(state["vqa_resident"])]
                 else:
                     choices = vqa_public(results)
             traj = [[tuple(s["bbox"]) for s in st.search_path] for st in states]
@@ -686,7 +686,7 @@ def vqa_probe(vqa, st2, peak_hbm, args):
     import torch
     eng = vqa.engine
     staged = st2["vqa_resident"]
-    q_ids, opt_ids, img_d, crops_d = staged[0]
+    q_ids, opt_ids, img_d, crops_d = staged[0][:4]
 
     def ev_time(fn, n=3):
         fn()
@@ -706,7 +706,10 @@ def vqa_probe(vqa, st2, peak_hbm, args):
 
     T = prefill()
     res = {"prompt_tokens": T, "prefill_ms": ev_time(prefill),
-           "option_scoring_ms": ev_time(lambda: eng.option_losses(q_ids, opt_ids, img_d, crops_d, [False], [True, True]))}
+           "option_scoring_ms": ev_time(lambda: eng.option_losses(q_ids, opt_ids, img_d, crops_d, [False], [True, True])),
+           "option_scoring_ms_per_question_batch_of_%d" % len(staged): ev_time(lambda: eng.option_losses_batch(staged)) / len(staged),
+           "how": "option scoring = CLIP + both projectors on 3 images, question prefill, ONE pass over all 4 options (segment-masked "
+                  "attention on the question's KV rows); batch = questions of equal spliced length share both passes"}
     wbytes = 2.0 * (32 * (4 * 4096 * 4096 + 3 * 4096 * 11008) + 32004 * 4096) if not args.tiny else None
     for B in (1, 8, 16):
         reqs = [(q_ids, img_d, crops_d, [False], [True, True])] * B

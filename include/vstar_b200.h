@@ -88,7 +88,9 @@ int vsb_copy2d_b16(const void* src, long long lds, void* dst, long long ldd, lon
  * they all end at row past+Tn; positions int32 [B*Tn] gives each new row its RoPE position and k_start int32 [B] the first
  * cache row of each sequence (requires Tn <= 4); both NULL for the aligned case.  tail_rows > 0: the caller will read only
  * the last tail_rows rows of every sequence, so the LAST layer runs attention / o-proj / MLP on those rows only (all other
- * rows of x are left at their layer n-1 value); 0 = every row.  8 kernel launches per layer. */
+ * rows of x are left at their layer n-1 value); 0 = every row.  q_seg int32 [B*Tn] (with positions): the new rows are several
+ * CONTINUATIONS of the cached prefix appended back to back (answer options, vstar_bench_eval.py:127-163): row r attends the
+ * prefix keys [0, seg_lo) and its own continuation from key q_seg[r] on (vsb_flash_attn_seg_bf16).  8 kernel launches per layer. */
 typedef struct {
   const void* ln1;
   const void* wqkv;
@@ -99,7 +101,7 @@ typedef struct {
 } vsb_llama_layer_t;
 int vsb_llama_layers(const vsb_llama_layer_t* layers, int n_layers, void* x, int B, int Tn, int past, void* cache, int Bc, int Tmax,
                      int d, int H, int inter, float rms_eps, const void* rope_cos, const void* rope_sin, const void* positions,
-                     const void* k_start, int tail_rows, void* scratch, void* stream);
+                     const void* k_start, int tail_rows, const void* q_seg, int seg_lo, void* scratch, void* stream);
 
 /* softmax(QK^T*scale [+causal]) V, head_dim 64/128; element (b,s,h,d) at base + b*bs + s*rs + h*D + d.
  * HF CLIP/OWL attention (modeling_clip.py:261-329) and Llama attention (modeling_llama.py:199-221). */
@@ -113,6 +115,12 @@ int vsb_flash_attn_bf16(const void* q, const void* k, const void* v, void* o, lo
 int vsb_attn_decode_bf16(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_rs, long long k_bs,
                          long long k_rs, long long v_bs, long long v_rs, long long o_bs, long long o_rs, int B, int H, int Sq, int Sk,
                          int D, int causal, float scale, const void* k_start, void* stream);
+/* Causal attention with a per-row segment mask: the Sq new rows occupy keys Sk-Sq..Sk-1; row r sees keys [0, seg_lo) and
+ * [q_seg[b*Sq + r], Sk-Sq+r].  One launch scores every answer option of a question on the question's cached K/V
+ * (the reference runs one forward per option on past_key_values, vstar_bench_eval.py:140-152). */
+int vsb_flash_attn_seg_bf16(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_rs, long long k_bs,
+                            long long k_rs, long long v_bs, long long v_rs, long long o_bs, long long o_rs, int B, int H, int Sq, int Sk,
+                            int D, float scale, const void* q_seg_i32, int seg_lo, void* stream);
 /* testing hook: 0 = auto (tcgen05 kernels for Sq >= 64, split-KV decode kernel for Sq <= 4, mma.sync kernel between),
  * 1 = mma.sync, 2 = tcgen05, 3 = tcgen05 single-tile kernel only, 4 = decode kernel */
 int vsb_attn_set_impl(int impl);

@@ -236,3 +236,36 @@ def test_model_adapter_runs_the_reference_call_sequence(setup):
         model(input_ids=torch.tensor([opts[0]]), past_key_values=out_q.past_key_values)
     with pytest.raises(NotImplementedError):
         model.generate(qt, images=image.half(), do_sample=True, temperature=0.7)
+
+
+def test_option_scoring_one_pass_and_batched(setup):
+    """every option of a question in ONE pass (segment-masked attention on the question's cached rows), questions of equal
+    length batched: (a) against the oracle's as-written variant (one forward per option on past_key_values) and its
+    full-recompute variant, (b) batch == one question at a time (bit-identical losses for the unbatched group, bf16-rounding
+    level for the batched one whose GEMMs pick other tile shapes)"""
+    V, O, cfg, sd, eng = setup
+    items, refs = [], []
+    for sub in ("short_long", "long_short"):
+        g = np.load(os.path.join(G, f"vqa_a_{sub}.npz"))
+        image, crops, q, opts, il, ol = inputs(g)
+        items.append((q[0].tolist(), [o.tolist() for o in opts], image.to(BF).cuda(), crops.to(BF).cuda(), il, ol))
+        refs.append((torch.from_numpy(g["option_losses"]), V.option_losses_cached(sd, cfg, q, opts, image, crops, il, ol)[0]))
+    # a third question with the same token count as the first (other pixels, other options of other lengths) => batched with it
+    g = np.load(os.path.join(G, "vqa_a_short_long.npz"))
+    image, crops, q, opts, il, ol = inputs(g)
+    gen = torch.Generator().manual_seed(99)
+    image3, crops3 = torch.randn(1, 3, 224, 224, generator=gen), torch.randn(2, 3, 224, 224, generator=gen)
+    opts3 = [torch.randint(3, cfg.vocab - 24, (n,), generator=gen) for n in (6, 1, 3)]
+    items.append((q[0].tolist(), [o.tolist() for o in opts3], image3.to(BF).cuda(), crops3.to(BF).cuda(), il, ol))
+    refs.append((None, V.option_losses_cached(sd, cfg, q, opts3, image3, crops3, il, ol)[0]))
+    single = [eng.option_losses_batch([it])[0] for it in items]
+    batch = eng.option_losses_batch(items)
+    for (gold, cached), (l1, c1), (lb, cb) in zip(refs, single, batch):
+        assert float((l1 - cached).abs().max()) < 5e-2, (l1, cached)
+        if gold is not None:
+            assert float((cached - gold).abs().max()) < 1e-4          # oracle variants agree with the reference's numbers
+        assert float((lb - l1).abs().max()) < 3e-2
+        srt = cached.sort().values
+        if float(srt[1] - srt[0]) > 0.08:
+            assert c1 == cb == int(cached.argmin())
+    assert torch.equal(batch[1][0], single[1][0])                     # the question that is alone in its length group

@@ -34,7 +34,8 @@ SIGNATURES = {
     "vsb_nll_rows_f32": [c_p, c_ll, c_i, c_i, c_p, c_p, c_p],
     "vsb_argmax_rows_f32": [c_p, c_ll, c_i, c_i, c_p, c_p, c_p],
     "vsb_copy2d_b16": [c_p, c_ll, c_p, c_ll, c_ll, c_i, c_p],
-    "vsb_llama_layers": [c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_i, c_p, c_p],
+    "vsb_llama_layers": [c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_i, c_p, c_i, c_p, c_p],
+    "vsb_flash_attn_seg_bf16": [c_p, c_p, c_p, c_p, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_i, c_p],
     "vsb_attn_decode_bf16": [c_p, c_p, c_p, c_p, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p],
     "vsb_flash_attn_bf16": [c_p, c_p, c_p, c_p, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
     "vsb_attn_set_impl": [c_i],

@@ -23,7 +23,7 @@ from collections import defaultdict
 
 import numpy as np
 
-from .seal import (choose_option, collect_search_results, expand2square_center, parse_missing_objects, smallest_size_for)
+from .seal import (choose_options, collect_search_results, expand2square_center, parse_missing_objects, smallest_size_for)
 from .visual_search import visual_search_many
 
 TEST_TYPES = ("direct_attributes", "relative_position")
@@ -97,10 +97,11 @@ def eval_model(args, vqa_llm=None, vsm=None, log=print, search_kwargs=None):
                 search_results, _ = visual_search_many(vsm, jobs, batch_size=search_batch, **(search_kwargs or {}))
                 for i, r in zip(owner, search_results):
                     found[i].append(r)
-            for smp, res in zip(chunk, found):
+            search_results = [collect_search_results(smp["missing"], res) if smp["missing"] else [] for smp, res in zip(chunk, found)]
+            chosen_all = choose_options(vqa_llm, [(smp["image"], smp["annotation"]["question"], smp["annotation"]["options"], smp["missing"], sr)
+                                                  for smp, sr in zip(chunk, search_results)])       # one batched option scoring
+            for smp, search_result, chosen in zip(chunk, search_results, chosen_all):
                 ann = smp["annotation"]
-                search_result = collect_search_results(smp["missing"], res) if smp["missing"] else []
-                chosen = choose_option(vqa_llm, smp["image"], ann["question"], ann["options"], smp["missing"], search_result)
                 correct = 1 if chosen == 0 else 0
                 per_type_acc[test_type].append(correct)
                 all_acc.append(correct)

@@ -47,6 +47,11 @@ struct AttnParams {
   int causal;      // query i attends keys j <= i + (Sk - Sq)
   float scale_log2;
   const int* k_start = nullptr;   // decode kernel only: first valid key of each batch entry (left-padded ragged batches)
+  // segment mask (mma.sync kernel only): query row r of batch b additionally does NOT see keys in [seg_lo, q_seg[b*Sq + r]).
+  // Several continuations of one cached prefix (the answer options of vstar_bench_eval.py:127-163) are appended back to back
+  // after the prefix and each row attends the prefix + the earlier rows of ITS OWN continuation only.
+  const int* q_seg = nullptr;
+  int seg_lo = 0;
 };
 
 constexpr int FA_BN = 64;
@@ -155,6 +160,11 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnParams p) {
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
       const int qrow0 = q0 + wrow + mt * 16 + g;
+      int seg[2] = {0, 0};
+      if (p.q_seg) {
+        seg[0] = (qrow0 < p.Sq) ? p.q_seg[(long long)b * p.Sq + qrow0] : 0;
+        seg[1] = (qrow0 + 8 < p.Sq) ? p.q_seg[(long long)b * p.Sq + qrow0 + 8] : 0;
+      }
       float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -163,7 +173,7 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnParams p) {
           const int key = key0 + i * 8 + 2 * t + (e & 1);
           const int qr = qrow0 + ((e >> 1) << 3);
           float x = s[mt][i][e] * p.scale_log2;
-          const bool masked = (key >= p.Sk) || (p.causal && key > qr + off);
+          const bool masked = (key >= p.Sk) || (p.causal && key > qr + off) || (key >= p.seg_lo && key < seg[e >> 1]);
           x = masked ? -INFINITY : x;
           s[mt][i][e] = x;
           mx[e >> 1] = fmaxf(mx[e >> 1], x);
@@ -513,6 +523,25 @@ extern "C" int vsb_attn_decode_bf16(const void* q, const void* k, const void* v,
   return D == 64 ? launch_decode<64>(pd, reinterpret_cast<cudaStream_t>(stream)) : launch_decode<128>(pd, reinterpret_cast<cudaStream_t>(stream));
 }
 
+static int launch_flash_mma(const AttnParams& p, int D, cudaStream_t st) {
+  if (D == 64) {
+    // (a 128-query-row variant, 2 m16 tiles per warp, measured slower on B200: 218 registers halve the occupancy)
+    const int smem = (64 + 4 * FA_BN) * 64 * 2;
+    static bool set64 = false;
+    if (!set64) { VSB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set64 = true; }
+    dim3 grid((p.Sq + 63) / 64, p.H, p.B);
+    flash_attn_kernel<64, 1><<<grid, 128, smem, st>>>(p);
+  } else {
+    const int smem = (64 + 4 * FA_BN) * 128 * 2;
+    static bool set128 = false;
+    if (!set128) { VSB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set128 = true; }
+    dim3 grid((p.Sq + 63) / 64, p.H, p.B);
+    flash_attn_kernel<128, 1><<<grid, 128, smem, st>>>(p);
+  }
+  VSB_LAUNCH_CHECK();
+  return VSB_OK;
+}
+
 extern "C" int vsb_flash_attn_bf16(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_rs,
                                    long long k_bs, long long k_rs, long long v_bs, long long v_rs, long long o_bs,
                                    long long o_rs, int B, int H, int Sq, int Sk, int D, int causal, float scale, void* stream) {
@@ -534,23 +563,31 @@ extern "C" int vsb_flash_attn_bf16(const void* q, const void* k, const void* v, 
   p.q_bs = q_bs; p.q_rs = q_rs; p.k_bs = k_bs; p.k_rs = k_rs; p.v_bs = v_bs; p.v_rs = v_rs; p.o_bs = o_bs; p.o_rs = o_rs;
   p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk; p.causal = causal;
   p.scale_log2 = scale * 1.4426950408889634f;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (D == 64) {
-    // (a 128-query-row variant, 2 m16 tiles per warp, measured slower on B200: 218 registers halve the occupancy)
-    const int smem = (64 + 4 * FA_BN) * 64 * 2;
-    static bool set64 = false;
-    if (!set64) { VSB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set64 = true; }
-    dim3 grid((Sq + 63) / 64, H, B);
-    flash_attn_kernel<64, 1><<<grid, 128, smem, st>>>(p);
-  } else {
-    const int smem = (64 + 4 * FA_BN) * 128 * 2;
-    static bool set128 = false;
-    if (!set128) { VSB_CUDA(cudaFuncSetAttribute(flash_attn_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set128 = true; }
-    dim3 grid((Sq + 63) / 64, H, B);
-    flash_attn_kernel<128, 1><<<grid, 128, smem, st>>>(p);
-  }
-  VSB_LAUNCH_CHECK();
-  return VSB_OK;
+  return launch_flash_mma(p, D, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Causal attention of several CONTINUATIONS of one cached prefix in one launch (answer-option scoring of the SEAL VQA LLM,
+// /root/reference/vstar_bench_eval.py:127-163, where the reference runs one forward per option on the question's
+// past_key_values): the Sq new rows sit at keys Sk-Sq .. Sk-1; row r sees keys 0..seg_lo-1 (the prefix) and
+// q_seg[b*Sq + r] .. (Sk-Sq+r) (the earlier rows of its own continuation).  mma.sync kernel (Sq is a few dozen rows).
+extern "C" int vsb_flash_attn_seg_bf16(const void* q, const void* k, const void* v, void* o, long long q_bs, long long q_rs,
+                                       long long k_bs, long long k_rs, long long v_bs, long long v_rs, long long o_bs,
+                                       long long o_rs, int B, int H, int Sq, int Sk, int D, float scale, const void* q_seg_i32, int seg_lo,
+                                       void* stream) {
+  VSB_CHECK_ARG(q && k && v && o && q_seg_i32, "vsb_flash_attn_seg_bf16: null pointer");
+  VSB_CHECK_ARG(D == 64 || D == 128, "vsb_flash_attn_seg_bf16: head_dim %d unsupported (64/128)", D);
+  VSB_CHECK_ARG(B > 0 && H > 0 && Sq > 0 && Sk >= Sq && seg_lo >= 0 && seg_lo <= Sk, "vsb_flash_attn_seg_bf16: bad shape");
+  VSB_CHECK_ARG(q_rs % 8 == 0 && k_rs % 8 == 0 && v_rs % 8 == 0 && o_rs % 8 == 0 && q_bs % 8 == 0 && k_bs % 8 == 0 &&
+                    v_bs % 8 == 0 && o_bs % 8 == 0,
+                "vsb_flash_attn_seg_bf16: strides must be multiples of 8 elements (16 B)");
+  AttnParams p;
+  p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v; p.o = (bf16*)o;
+  p.q_bs = q_bs; p.q_rs = q_rs; p.k_bs = k_bs; p.k_rs = k_rs; p.v_bs = v_bs; p.v_rs = v_rs; p.o_bs = o_bs; p.o_rs = o_rs;
+  p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk; p.causal = 1;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.q_seg = reinterpret_cast<const int*>(q_seg_i32);
+  p.seg_lo = seg_lo;
+  return launch_flash_mma(p, D, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vsb_attn_small_bf16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o,

@@ -24,7 +24,8 @@ int vsb_flash_attn_tc(const void* q, const void* k, const void* v, void* o, long
 
 extern "C" int vsb_llama_layers(const vsb_llama_layer_t* layers, int n_layers, void* x, int B, int Tn, int past, void* cache, int Bc,
                                 int Tmax, int d, int H, int inter, float rms_eps, const void* rope_cos, const void* rope_sin,
-                                const void* positions, const void* k_start, int tail_rows, void* scratch, void* stream) {
+                                const void* positions, const void* k_start, int tail_rows, const void* q_seg, int seg_lo, void* scratch,
+                                void* stream) {
   VSB_CHECK_ARG(layers && x && cache && rope_cos && rope_sin && scratch, "vsb_llama_layers: null pointer");
   VSB_CHECK_ARG(n_layers > 0 && B > 0 && Tn > 0 && past >= 0 && d > 0 && H > 0 && inter > 0, "vsb_llama_layers: bad shape");
   VSB_CHECK_ARG(B <= Bc && past + Tn <= Tmax, "vsb_llama_layers: B=%d Tn=%d past=%d exceed the cache [%d, %d]", B, Tn, past, Bc, Tmax);
@@ -41,6 +42,7 @@ extern "C" int vsb_llama_layers(const vsb_llama_layer_t* layers, int n_layers, v
   // tail mode: the caller consumes only the last `tail_rows` rows of every sequence (answer-predicting rows and the [LOC]
   // row of the guided search).  K/V of the last layer are needed by nobody else, so that layer runs its attention,
   // o-projection and MLP over B*tail rows only (same kernels, same per-row arithmetic => same values on those rows).
+  VSB_CHECK_ARG(q_seg == nullptr || (k_start == nullptr && tail_rows == 0), "vsb_llama_layers: q_seg excludes k_start / tail_rows");
   const bool tail = tail_rows > 0 && 2 * tail_rows <= Tn && k_start == nullptr && (hd == 64 || hd == 128);
   for (int li = 0; li < n_layers; ++li) {
     const vsb_llama_layer_t& L = layers[li];
@@ -63,7 +65,10 @@ extern "C" int vsb_llama_layers(const vsb_llama_layer_t* layers, int n_layers, v
       VSB_TRY(vsb_copy2d_b16(xt, (long long)tail_rows * d, xb + (long long)(Tn - tail_rows) * d, (long long)Tn * d, B, tail_rows * d, stream));
       break;
     }
-    if (k_start != nullptr)
+    if (q_seg != nullptr)
+      VSB_TRY(vsb_flash_attn_seg_bf16(cl + (long long)past * ld, cl + d, cl + 2 * d, attn, (long long)Tmax * ld, ld, (long long)Tmax * ld, ld,
+                                      (long long)Tmax * ld, ld, (long long)Tn * d, d, B, H, Tn, past + Tn, hd, scale, q_seg, seg_lo, stream));
+    else if (k_start != nullptr)
       VSB_TRY(vsb_attn_decode_bf16(cl + (long long)past * ld, cl + d, cl + 2 * d, attn, (long long)Tmax * ld, ld, (long long)Tmax * ld, ld,
                                    (long long)Tmax * ld, ld, (long long)Tn * d, d, B, H, Tn, past + Tn, hd, 1, scale, k_start, stream));
     else

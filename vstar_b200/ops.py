@@ -62,22 +62,25 @@ def llama_layer_table(layers):
 
 
 def llama_layers(table, n_layers, x, B, Tn, past, cache, Bc, Tmax, d, H, inter, eps, rope_cos, rope_sin, scratch, positions=None,
-                 k_start=None, cache_row_offset=0, tail_rows=0):
+                 k_start=None, cache_row_offset=0, tail_rows=0, q_seg=None, seg_lo=0):
     """whole decoder stack in ONE native call (csrc/llama_layers.cu): in place on x [B*Tn, d].
     cache_row_offset shifts the cache origin by that many [3d] rows (a sequence placed at batch slot b, first row s:
     b*Tmax + s) so a single sequence can be prefilled anywhere in a shared cache; positions / k_start: ragged decode;
-    tail_rows > 0: only the last tail_rows rows of every sequence are valid on return (the last layer skips the others)."""
+    tail_rows > 0: only the last tail_rows rows of every sequence are valid on return (the last layer skips the others);
+    q_seg int32 [B*Tn] + seg_lo: the new rows are several continuations of the cached prefix [0, seg_lo) appended back to back;
+    row r attends the prefix and its own continuation from key q_seg[r] on."""
     _chk(x, BF16), _chk(cache, BF16), _chk(scratch, BF16)
     assert x.is_contiguous() and cache.is_contiguous() and x.shape == (B * Tn, d)
     assert scratch.numel() >= B * Tn * (2 * d + inter)
-    for t in (positions, k_start):
+    for t in (positions, k_start, q_seg):
         assert t is None or (t.dtype == torch.int32 and t.is_contiguous() and t.is_cuda)
+    assert q_seg is None or (q_seg.numel() == B * Tn and positions is not None)
     assert positions is None or positions.numel() == B * Tn
     assert k_start is None or k_start.numel() == B
     _lib.launches += 8 * n_layers + (2 if (tail_rows > 0 and 2 * tail_rows <= Tn and k_start is None) else 0)
     call("vsb_llama_layers", table, n_layers, x.data_ptr(), B, Tn, past, cache.data_ptr() + cache_row_offset * 3 * d * 2, Bc, Tmax, d, H,
-         inter, float(eps), rope_cos.data_ptr(), rope_sin.data_ptr(), _p(positions), _p(k_start), int(tail_rows), scratch.data_ptr(),
-         _stream())
+         inter, float(eps), rope_cos.data_ptr(), rope_sin.data_ptr(), _p(positions), _p(k_start), int(tail_rows), _p(q_seg), int(seg_lo),
+         scratch.data_ptr(), _stream())
     return x
 
 

@@ -74,9 +74,23 @@ def collect_search_results(missing, results):
 
 def choose_option(vqa_llm, image, question, options, missing, search_result):
     """vstar_bench_eval.py:226-257: option scoring, with the searched objects spliced in as <object> features"""
+    return vqa_llm.multiple_choices_inference(*option_request(vqa_llm, image, question, options, missing, search_result))
+
+
+def choose_options(vqa_llm, samples):
+    """choose_option for several samples [(image, question, options, missing, search_result)]: one batched option scoring when
+    the VQA LLM offers it (`multiple_choices_inference_batch`), the reference's one-at-a-time calls otherwise"""
+    reqs = [option_request(vqa_llm, *s) for s in samples]
+    if hasattr(vqa_llm, "multiple_choices_inference_batch") and len(reqs) > 1:
+        return vqa_llm.multiple_choices_inference_batch(reqs)
+    return [vqa_llm.multiple_choices_inference(*r) for r in reqs]
+
+
+def option_request(vqa_llm, image, question, options, missing, search_result):
+    """-> the argument tuple (image, question, options, object_crops, images_long, objects_long) of multiple_choices_inference"""
     if not missing:
         # the reference scores the options on the re-opened, UNPADDED image here (vstar_bench_eval.py:227, :257)
-        return vqa_llm.multiple_choices_inference(image, question, options)
+        return (image, question, options, None, None, None)
     bg = tuple(int(x * 255) for x in vqa_llm.image_processor.image_mean)
     padded, left, top = expand2square_center(image, bg)
     names = [r["name"] for r in search_result]
@@ -85,8 +99,7 @@ def choose_option(vqa_llm, image, question, options, missing, search_result):
     crops = torch.stack([vqa_llm.get_object_crop(image, b, patch_scale=1.2) for b in boxes], 0)
     shifted = [[b[0] + left, b[1] + top, b[2], b[3]] for b in boxes]
     nboxes = [normalize_bbox(b, padded.width, padded.height) for b in shifted]
-    return vqa_llm.multiple_choices_inference(padded, focus_question(question, names, nboxes), options, crops,
-                                              images_long=[False], objects_long=objects_long)
+    return (padded, focus_question(question, names, nboxes), options, crops, [False], objects_long)
 
 
 def seal_answer(vqa_llm, vsm, image, question, options, minimum_size_scale=4.0, minimum_size=224, search_batch=16,

@@ -127,11 +127,10 @@ class VQAEngine(LlamaClipCore):
     # ------------------------------------------------------------------ splice (llava_search_arch.py:139-216)
     def build_embeds(self, input_ids, image, object_crops=None, images_long=None, objects_long=None):
         """input_ids: python list with one -200 and k -300 placeholders -> embeds [T, d] on the device"""
+        return self.build_embeds_batch([(input_ids, image, object_crops, images_long, objects_long)])[0]
+
+    def _splice(self, ids, img_long, img_short, obj_long, obj_short, images_long, objects_long):
         c = self.cfg
-        ids = list(input_ids)
-        img_long, img_short = self.project_both(image)
-        if object_crops is not None and len(object_crops) > 0:
-            obj_long, obj_short = self.project_both(object_crops)
         segs = []                                   # ("ids", list) | ("feat", tensor [m,d])
         s = ids.index(IMAGE_TOKEN_INDEX)
         use_long = images_long is None or bool(images_long[0])
@@ -264,22 +263,88 @@ class VQAEngine(LlamaClipCore):
         return outs
 
     def option_losses(self, question_ids, options_ids, image, object_crops=None, images_long=None, objects_long=None):
-        """multiple_choices_inference core (vstar_bench_eval.py:127-163): the question prefix is prefilled ONCE; every
-        option is appended on top of the cached prefix (its rows overwrite the previous option's) and scored by the mean
-        token NLL.  Returns (losses fp32 [n_options] on host, argmin)."""
-        x = self.build_embeds(question_ids, image, object_crops, images_long, objects_long)
-        Tq = x.shape[0]
-        self.prefill_embeds(x)
-        q_last = self.last_logits(x)                                  # predicts the first option token
-        losses = []
-        for opt in options_ids:
-            opt = list(opt)
-            lg = self.append_tokens(opt, Tq)                           # [n, V]; row i predicts token i+1
-            rows = torch.cat([q_last, lg[:-1]], dim=0).contiguous()
-            nll = ops.nll_rows(rows, torch.tensor(opt, dtype=torch.int64, device=self.dev))
-            losses.append(nll.mean())
-        losses = torch.stack(losses).cpu()
-        return losses, int(losses.argmin())
+        """multiple_choices_inference core (vstar_bench_eval.py:127-163).  Returns (losses fp32 [n_options] on host, argmin)."""
+        return self.option_losses_batch([(question_ids, options_ids, image, object_crops, images_long, objects_long)])[0]
+
+    def build_embeds_batch(self, items):
+        """items: [(input_ids, image [1,3,224,224], object_crops [k,3,224,224] | None, images_long, objects_long)] -> list of
+        embeds [T_i, d].  ONE CLIP + projector pass over every image and object crop of the batch."""
+        c = self.cfg
+        pix, spans = [], []
+        for ids, image, crops, il, ol in items:
+            k = 0 if crops is None else int(crops.shape[0])
+            spans.append((len(pix), k))
+            pix.append(image)
+            if k:
+                pix.append(crops)
+        allp = torch.cat(pix, 0).contiguous() if len(pix) > 1 else pix[0]
+        long_all, short_all = self.project_both(allp)
+        nl, ns = c.clip_tokens, self.NLAT
+        out, img_i = [], 0
+        for (ids, image, crops, il, ol) in items:
+            k = 0 if crops is None else int(crops.shape[0])
+            img_long, img_short = long_all[img_i * nl:(img_i + 1) * nl], short_all[img_i * ns:(img_i + 1) * ns]
+            obj_long, obj_short = long_all[(img_i + 1) * nl:(img_i + 1 + k) * nl], short_all[(img_i + 1) * ns:(img_i + 1 + k) * ns]
+            img_i += 1 + k
+            out.append(self._splice(list(ids), img_long, img_short, obj_long, obj_short, il, ol))
+        return out
+
+    def option_losses_batch(self, items):
+        """Option scoring for several questions: items = [(question_ids, options_ids, image, object_crops, images_long,
+        objects_long)] -> [(losses fp32 [n_options] on host, argmin)].
+
+        The reference prefills the question once and then runs ONE FORWARD PER OPTION on its past_key_values
+        (vstar_bench_eval.py:140-152).  Here every option of a question is scored in ONE pass: the options' tokens are
+        appended back to back after the question's cache rows, every row carries its own RoPE position (Tq + index inside its
+        option) and the attention masks the other options' rows (vsb_flash_attn_seg_bf16), so each row sees exactly the keys
+        it sees in the reference.  Questions whose spliced length is equal are batched: one prefill with M = G*Tq rows and
+        one option pass for all of them (each weight byte is read twice per GROUP instead of five times per question)."""
+        embeds = self.build_embeds_batch([(q, img, crops, il, ol) for q, opts, img, crops, il, ol in items])
+        groups = {}
+        for i, x in enumerate(embeds):
+            groups.setdefault(int(x.shape[0]), []).append(i)
+        results = [None] * len(items)
+        dev = self.dev
+        for Tq, members in groups.items():
+            G = len(members)
+            opts = [[list(o) for o in items[i][1]] for i in members]
+            Tn = max(sum(len(o) for o in oo) for oo in opts)
+            self._ensure_cache(G, self._capacity(Tq + Tn))
+            self._prefix_slots = 0
+            x = torch.cat([embeds[i] for i in members], 0).contiguous() if G > 1 else embeds[members[0]]
+            self._llm_layers(x, G, Tq, 0, self.max_tokens)
+            self.kv_epoch = getattr(self, "kv_epoch", 0) + 1
+            last = torch.tensor([g * Tq + Tq - 1 for g in range(G)], dtype=torch.int64, device=dev)
+            _, _, q_last = self._logits_rows(x, last)                          # [G, V]: predicts the first token of every option
+            # appended rows: options back to back, right-padded to Tn with rows that see only themselves
+            ids = torch.zeros((G, Tn), dtype=torch.int64)
+            pos = torch.zeros((G, Tn), dtype=torch.int32)
+            seg = torch.zeros((G, Tn), dtype=torch.int32)
+            pred, labels, spans = [], [], []
+            for g, oo in enumerate(opts):
+                off = 0
+                for o in oo:
+                    spans.append((g, len(labels), len(o)))
+                    for j, tok in enumerate(o):
+                        ids[g, off + j], pos[g, off + j], seg[g, off + j] = tok, Tq + j, Tq + off
+                        pred.append(g if j == 0 else G + g * Tn + off + j - 1)
+                        labels.append(tok)
+                    off += len(o)
+                for r in range(off, Tn):
+                    pos[g, r], seg[g, r] = Tq, Tq + r
+            xo = ops.gather_rows(ids.view(-1).to(dev), self.w.embed)
+            self._llm_layers(xo, G, Tn, Tq, self.max_tokens, positions=pos.view(-1).to(dev), q_seg=seg.view(-1).to(dev), seg_lo=Tq)
+            hn = ops.rmsnorm(xo, self.w.final_norm, self.cfg.rms_eps)
+            lo = ops.gemm(hn, self.w.lm_head, out_dtype=torch.float32)
+            rows = torch.cat([q_last, lo], 0).index_select(0, torch.tensor(pred, dtype=torch.int64, device=dev)).contiguous()
+            nll = ops.nll_rows(rows, torch.tensor(labels, dtype=torch.int64, device=dev)).cpu()
+            per = {}
+            for g, s0, n in spans:
+                per.setdefault(g, []).append(nll[s0:s0 + n].mean())
+            for g, i in enumerate(members):
+                losses = torch.stack(per[g])
+                results[i] = (losses, int(losses.argmin()))
+        return results
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -484,8 +549,7 @@ class VQA_LLM:
             texts.append(text.strip())
         return texts
 
-    @torch.inference_mode()
-    def multiple_choices_inference(self, image, question, options, object_crops=None, images_long=None, objects_long=None):
+    def _choice_item(self, image, question, options, object_crops, images_long, objects_long):
         qs = DEFAULT_IMAGE_TOKEN + "\n" + question
         q_ids = tokenizer_image_object_token(build_prompt_v1(qs), self.tokenizer)
         opt_ids = []
@@ -493,5 +557,16 @@ class VQA_LLM:
             full = tokenizer_image_object_token(build_prompt_v1(qs, option), self.tokenizer)
             opt_ids.append(full[len(q_ids):])
         img, crops = self._pixels(image, object_crops)
-        losses, choice = self.engine.option_losses(q_ids, opt_ids, img, crops, images_long, objects_long)
-        return choice
+        return (q_ids, opt_ids, img, crops, images_long, objects_long)
+
+    @torch.inference_mode()
+    def multiple_choices_inference(self, image, question, options, object_crops=None, images_long=None, objects_long=None):
+        item = self._choice_item(image, question, options, object_crops, images_long, objects_long)
+        return self.engine.option_losses_batch([item])[0][1]
+
+    @torch.inference_mode()
+    def multiple_choices_inference_batch(self, requests):
+        """requests: [(image, question, options, object_crops, images_long, objects_long)] -> [chosen option index].
+        Not in the reference (one sample at a time, vstar_bench_eval.py:257): same per-sample result, batched execution."""
+        items = [self._choice_item(*r) for r in requests]
+        return [c for _, c in self.engine.option_losses_batch(items)]
