@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around the timed resident steps (for ncu)")
     ap.add_argument("--no-prefix-cache", action="store_true",
                     help="recompute the K/V rows of the constant text prefix (system prompt before <im_start>) for every crop")
+    ap.add_argument("--gemm-l2-hints", type=int, default=1, help="A/B switch for vsb_gemm_set_l2_hints (1 = production)")
     ap.add_argument("--depth", type=int, default=2, help="frontier batches in flight (1 = round-1 style synchronous rounds)")
     return ap.parse_args()
 
@@ -73,10 +74,10 @@ def peaks():
 
 def gemm_traffic_from_profile():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant GEMM launch, read from the newest committed ncu export of
-    the CURRENT kernel (profiles/r*_gemm_dram_bytes*.csv, written by tools/prof_gemm.py under ncu); None if there is none"""
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_dram_bytes*.csv")))
+    the CURRENT kernel (profiles/rNN_gemm_dram_bytes.csv, written by tools/prof_gemm.py under ncu); None if there is none"""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9]_gemm_dram_bytes.csv")))
     if not files:
-        return None, "no profiles/r*_gemm_dram_bytes*.csv committed"
+        return None, "no profiles/rNN_gemm_dram_bytes.csv committed"
     path = files[-1]
     unit_scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     per_id = {}
@@ -355,6 +356,8 @@ def run_b200(args):
 
     if args.attn_impl:
         _lib.call("vsb_attn_set_impl", args.attn_impl)
+    if not args.gemm_l2_hints:
+        _lib.call("vsb_gemm_set_l2_hints", 0)
     cfg = tiny_config() if args.tiny else VSMConfig()
     t0 = time.time()
 
@@ -396,6 +399,8 @@ def run_b200(args):
 
     vsm = BenchVSM(engine=engine, forced_answer_ids=ans.tolist(), frontier_batch=args.batch)
     vqa = None if args.no_vqa else VQA_LLM(engine=VQAEngine(vqa_weights))
+    if vqa is not None:
+        vqa.use_device_images(vsm)        # option-scoring pixels are cut / resized on the GPU from the resident search image
     load_s = time.time() - t0
     kw = dict(confidence_high=2.0, target_cue_threshold=-1e9, target_cue_threshold_minimum=-1e9)
 
@@ -430,18 +435,10 @@ def run_b200(args):
         def stage_vqa(results):
             """device-resident inputs of the same option scorings (built once from a warm-up run; searches are deterministic)"""
             staged = []
-            bg = tuple(int(x * 255) for x in vqa.image_processor.image_mean)
             for im, r in zip(images, results):
                 sr = search_result_of(r)
-                padded, left, top = seal.expand2square_center(im, bg)
-                crops = torch.stack([vqa.get_object_crop(im, s["bbox"], patch_scale=1.2) for s in sr], 0)
-                nb = [seal.normalize_bbox([s["bbox"][0] + left, s["bbox"][1] + top, s["bbox"][2], s["bbox"][3]], padded.width, padded.height)
-                      for s in sr]
-                qs = "<image>\n" + seal.focus_question(QUESTION, [s["name"] for s in sr], nb)
-                q_ids = tokenizer_image_object_token(build_prompt_v1(qs), vqa.tokenizer)
-                opt_ids = [tokenizer_image_object_token(build_prompt_v1(qs, o), vqa.tokenizer)[len(q_ids):] for o in OPTIONS]
-                img_d, crops_d = vqa._pixels(padded, crops)
-                staged.append((q_ids, opt_ids, img_d, crops_d, [False], [True, True]))
+                req = seal.option_request(vqa, im, QUESTION, OPTIONS, list(TARGETS), sr)
+                staged.append(vqa._choice_item(*req))
             return staged
 
         def step(resident):
@@ -501,9 +498,9 @@ def run_b200(args):
     e2e_ms, e2e_crops = timed_steps(step2, args.steps, False)
     bytes_h2d = (vsm.h2d_bytes - h2d0) // args.steps
     bytes_d2h = (vsm.d2h_bytes - d2h0) // args.steps
-    if vqa is not None:      # VQA leg: 3 fp32 pixel tensors [3,224,224] up per search, 4 option losses down
-        bytes_h2d += args.searches * 3 * 3 * 224 * 224 * 4
-        bytes_d2h += args.searches * 4 * 4
+    if vqa is not None:      # VQA leg: pixels come from the resident search image (no extra H2D); prompt ids up, 4 option NLL vectors down
+        bytes_h2d += args.searches * 8 * 700
+        bytes_d2h += args.searches * 4 * 40
 
     # ---- device-resident leg
     for _ in range(max(1, args.warmup)):
@@ -539,6 +536,7 @@ def run_b200(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                      "traffic": traffic, "traffic_note": traffic_note, "kernel": "gemm_bf16_tcgen05_kernel", "launches": gemm_n,
+                     "gemm_time_share_of_step": gemm_ms / dev_ms if dev_ms > 0 else None,
                      "how": "sum(2*M*N*K) / sum(CUDA-event duration) over every GEMM launch of the timed region (VSM and VQA); peak = " + peak_src,
                      "whole_path_frac": value / world * flops_per_crop / (peak_tf * 1e12),
                      "whole_path_note": ("crops/s/GPU x %.2f TFLOP/crop executed / peak; conservative: the VQA option scoring inside the step "

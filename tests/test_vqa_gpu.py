@@ -269,3 +269,41 @@ def test_option_scoring_one_pass_and_batched(setup):
         if float(srt[1] - srt[0]) > 0.08:
             assert c1 == cb == int(cached.argmin())
     assert torch.equal(batch[1][0], single[1][0])                     # the question that is alone in its length group
+
+
+def test_device_pixels_equal_host_preprocessing(setup):
+    """VQA_LLM.device_pixels (GPU crop / centred padding / Pillow-exact bicubic / normalise from the resident search image) ==
+    the reference's host path (expand2square + CLIPImageProcessor + get_object_crop, vstar_bench_eval.py:25-76, :228-256), bit
+    for bit, for square, wide and tall images"""
+    from PIL import Image
+    from vstar_b200 import seal
+    from vstar_b200.image import GpuImagePipeline
+    from vstar_b200.vqa import VQA_LLM
+    V, O, cfg, sd, eng = setup
+
+    class Src:                                   # what VQA_LLM needs from a VSM: the pipeline and the resident-image cache
+        def __init__(self):
+            self.pipeline = GpuImagePipeline("cuda", 224, 768)
+
+        def resident(self, im):
+            return self.pipeline.upload(im)
+
+    vqa = VQA_LLM(engine=eng)
+    host = VQA_LLM(engine=eng)
+    vqa.use_device_images(Src())
+    for k, (w, h) in enumerate([(640, 640), (900, 500), (333, 777)]):
+        img = Image.fromarray(np.random.default_rng(60 + k).integers(0, 256, (h, w, 3), dtype=np.uint8), "RGB")
+        boxes = [[w * 0.3, h * 0.4, w * 0.1, h * 0.12], [w * 0.62, h * 0.2, 30.5, 41.2], [2.0, 3.0, 500.0, 600.0]]
+        img_d, crops_d = vqa.device_pixels(img, boxes, patch_scale=1.2)
+        bg = tuple(int(x * 255) for x in host.image_processor.image_mean)
+        padded, _, _ = seal.expand2square_center(img, bg)
+        crops_h = torch.stack([host.get_object_crop(img, b, patch_scale=1.2) for b in boxes], 0)
+        img_h, crops_hd = host._pixels(padded, crops_h)
+        torch.cuda.synchronize()
+        assert torch.equal(img_d, img_h), (w, h, float((img_d.float() - img_h.float()).abs().max()))
+        assert torch.equal(crops_d, crops_hd), (w, h, float((crops_d.float() - crops_hd.float()).abs().max()))
+    # and the request built by seal.option_request is the same question / flags either way
+    sr = [{"bbox": boxes[0], "name": "mug"}, {"bbox": boxes[1], "name": "cup"}]
+    a = seal.option_request(vqa, img, "q?", ["x", "y"], ["mug", "cup"], sr)
+    b = seal.option_request(host, img, "q?", ["x", "y"], ["mug", "cup"], sr)
+    assert a[1] == b[1] and a[4:] == b[4:] and a[0].is_cuda and not torch.is_tensor(b[0])

@@ -21,6 +21,7 @@ SIGNATURES = {
     "vsb_gemm_profile_end": [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_ll)],
     "vsb_gemm_set_tuning": [c_i, c_i],
     "vsb_gemm_set_group_m": [c_i],
+    "vsb_gemm_set_l2_hints": [c_i],
     "vsb_layernorm_bf16": [c_p, c_ll, c_p, c_p, c_p, c_ll, c_i, c_i, c_f, c_i, c_p],
     "vsb_rmsnorm_bf16": [c_p, c_ll, c_p, c_p, c_ll, c_i, c_i, c_f, c_p],
     "vsb_rope_bf16": [c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_ll, c_ll, c_p],

@@ -64,6 +64,8 @@ def eval_model(args, vqa_llm=None, vsm=None, log=print, search_kwargs=None):
         vsm_args = parse_args({})
         vsm_args.version = args.vsm_model_path
         vsm = VSM(vsm_args)
+    if hasattr(vqa_llm, "use_device_images") and getattr(vsm, "pipeline", None) is not None:
+        vqa_llm.use_device_images(vsm)         # option-scoring pixels from the search image that is already resident in HBM
     in_flight = max(1, int(getattr(args, "images_in_flight", 8)))
     search_batch = int(getattr(args, "search_batch", 64))
     bg = tuple(int(x * 255) for x in vqa_llm.image_processor.image_mean)

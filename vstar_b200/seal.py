@@ -91,14 +91,20 @@ def option_request(vqa_llm, image, question, options, missing, search_result):
     if not missing:
         # the reference scores the options on the re-opened, UNPADDED image here (vstar_bench_eval.py:227, :257)
         return (image, question, options, None, None, None)
-    bg = tuple(int(x * 255) for x in vqa_llm.image_processor.image_mean)
-    padded, left, top = expand2square_center(image, bg)
     names = [r["name"] for r in search_result]
     boxes = deepcopy([r["bbox"] for r in search_result])
     objects_long = [True] * len(names) if len(names) <= 2 else [False] * len(names)
-    crops = torch.stack([vqa_llm.get_object_crop(image, b, patch_scale=1.2) for b in boxes], 0)
+    side = max(image.width, image.height)
+    left, top = (side - image.width) // 2, (side - image.height) // 2          # expand2square (vstar_bench_eval.py:25-36)
     shifted = [[b[0] + left, b[1] + top, b[2], b[3]] for b in boxes]
-    nboxes = [normalize_bbox(b, padded.width, padded.height) for b in shifted]
+    nboxes = [normalize_bbox(b, side, side) for b in shifted]
+    if getattr(vqa_llm, "_img_src", None) is not None:
+        # padded image + object crops cut and resized on the GPU from the resident search image (bit-identical pixels)
+        padded, crops = vqa_llm.device_pixels(image, boxes, patch_scale=1.2)
+    else:
+        bg = tuple(int(x * 255) for x in vqa_llm.image_processor.image_mean)
+        padded, _, _ = expand2square_center(image, bg)
+        crops = torch.stack([vqa_llm.get_object_crop(image, b, patch_scale=1.2) for b in boxes], 0)
     return (padded, focus_question(question, names, nboxes), options, crops, [False], objects_long)
 
 

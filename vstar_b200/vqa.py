@@ -480,6 +480,8 @@ class VQA_LLM:
         self.conv_type = conv_type
         self.eos = getattr(self.tokenizer, "eos_token_id", 2)
 
+    _img_src = None
+
     def get_patch(self, bbox, image_width, image_height, patch_size=224, patch_scale=None):
         object_width = int(np.ceil(bbox[2]))
         object_height = int(np.ceil(bbox[3]))
@@ -501,11 +503,45 @@ class VQA_LLM:
         return _clip_preprocess(crop)
 
     def _pixels(self, image, object_crops):
+        if torch.is_tensor(image) and image.is_cuda:            # already preprocessed on the device (device_pixels)
+            return image, object_crops
         img = _clip_preprocess(image).unsqueeze(0).to(self.engine.dev)
         img = ops.cast_f32_bf16(img.contiguous())
         crops = None
         if object_crops is not None and len(object_crops) > 0:
             crops = ops.cast_f32_bf16(torch.as_tensor(object_crops).float().to(self.engine.dev).contiguous())
+        return img, crops
+
+    def use_device_images(self, vsm):
+        """share the VSM's resident search images and its Pillow-exact GPU resize pipeline: the padded image and the object
+        crops of the option-scoring prompt (vstar_bench_eval.py:228-256) are then cut and resized on the device from the
+        image that is already in HBM - bit-identical pixels, no host PIL work between the search and the answer"""
+        self._img_src = vsm
+
+    def device_pixels(self, image, boxes, patch_scale=1.2):
+        """== (_clip_preprocess(expand2square_center(image)), [get_object_crop(image, b, patch_scale) for b in boxes]) as bf16
+        device tensors ([1,3,224,224], [k,3,224,224] or None), computed by the GPU image pipeline"""
+        vsm = self._img_src
+        pipe = vsm.pipeline
+        res = vsm.resident(image)                                   # uint8 [H, W, 3] in HBM
+        H, W = int(res.shape[0]), int(res.shape[1])
+        side = max(W, H)
+        dev = self.engine.dev
+        img = torch.empty((1, 3, 224, 224), dtype=BF, device=dev)
+        if W == H:
+            src = res
+        else:                                                       # centred padding (vstar_bench_eval.py:25-36)
+            bg = torch.tensor([int(x * 255) for x in self.image_processor.image_mean], dtype=torch.uint8, device=dev)
+            src = bg.view(1, 1, 3).expand(side, side, 3).contiguous()
+            left, top = (side - W) // 2, (side - H) // 2
+            src[top:top + H, left:left + W] = res
+        pipe._resize(src, 0, 0, side, side, side, side, 224, 224, out_bf16=img[0])
+        crops = None
+        if boxes is not None and len(boxes) > 0:
+            crops = torch.empty((len(boxes), 3, 224, 224), dtype=BF, device=dev)
+            for i, b in enumerate(boxes):
+                l, t, r, btm = self.get_patch(b, W, H, patch_scale=patch_scale)
+                pipe._resize(res, l, t, r - l, btm - t, r - l, btm - t, 224, 224, out_bf16=crops[i])
         return img, crops
 
     @torch.inference_mode()

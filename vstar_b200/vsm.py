@@ -313,7 +313,11 @@ class VSM:
             # group is cut into chunks whose engine work is launched WITHOUT waiting for the GPU (defer=True), so the host
             # converts the next chunk's images while the GPU evaluates the previous one.
             fresh = sum(1 for i in members if self.prep == "gpu" and id(regions[i][0]) not in self._resident)
-            step = self.upload_chunk if (0 < self.upload_chunk < min(fresh, len(members))) else len(members)
+            step = len(members)
+            if self.upload_chunk > 0 and fresh >= 4:
+                # at least two chunks when several images still have to be uploaded: the first engine call starts after half of
+                # the conversions instead of all of them
+                step = max(2, min(self.upload_chunk, (len(members) + 1) // 2))
             for c0 in range(0, len(members), step):
                 chunk = members[c0:c0 + step]
                 ic, io = self._prep_regions([regions[i] for i in chunk])
