@@ -48,7 +48,8 @@ int vsb_gemm_profile_end(double* flops, double* ms, long long* launches);
  * 256x256 cluster tiles, 0 = auto) and the CTA count (0 = #SMs); tile-rasterisation band height in m-blocks (0 = auto) */
 int vsb_gemm_set_tuning(int force_bn, int max_ctas);
 int vsb_gemm_set_group_m(int group_m);
-/* 1 (default) = L2 eviction priorities on the 2-CTA kernel: A band evict_last, W tiles evict_first, streaming output stores; 0 = none */
+/* L2 eviction hints of the 2-CTA kernel, bit mask: 1 = A tiles evict_last, 2 = W tiles evict_first, 8 = W tiles evict_last,
+ * 4 = streaming (.cs) output stores; 0 = none.  The default is the setting that minimised dram__bytes on B200. */
 int vsb_gemm_set_l2_hints(int on);
 
 /* nn.LayerNorm over the last dim (fp32 stats), optional fused activation (VSB_EPI_NONE / VSB_EPI_GELU).

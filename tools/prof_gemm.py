@@ -22,9 +22,19 @@ w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(BF)
 out = torch.empty(M, N // 2, dtype=BF, device="cuda")
 from vstar_b200 import _lib  # noqa: E402
 
-# launches 0-2: L2 eviction hints OFF (round-1 behaviour); launches 3-5: hints ON (shipped default) -> bench.py reads the LAST one
-for hints in (0, 1):
-    _lib.call("vsb_gemm_set_l2_hints", hints)
+# sweep (env PROF_GEMM_SWEEP=1): every hint mask x band height, 2 launches each; otherwise 3 launches of the shipped default
+if os.environ.get("PROF_GEMM_SWEEP"):
+    k = 0
+    for gm in (16, 24, 8):
+        _lib.call("vsb_gemm_set_group_m", gm)
+        for mask in (0, 1, 4, 5, 8, 9, 12, 13):
+            _lib.call("vsb_gemm_set_l2_hints", mask)
+            for _ in range(2):
+                ops.gemm(a, w, out=out, epilogue=ops.EPI_SWIGLU)
+            torch.cuda.synchronize()
+            print(f"launches {k}-{k + 1}: group_m={gm} hint_mask={mask}")
+            k += 2
+else:
     for _ in range(3):
         ops.gemm(a, w, out=out, epilogue=ops.EPI_SWIGLU)
     torch.cuda.synchronize()

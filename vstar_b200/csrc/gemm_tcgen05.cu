@@ -902,7 +902,7 @@ int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams&
   return VSB_OK;
 }
 
-int g_l2_hints = 1;      // 1 = A evict_last / W evict_first / streaming output stores on the large (2-CTA) problems; 0 = none
+int g_l2_hints = 4;      // bit mask of L2 eviction hints on the 2-CTA kernel; 4 (streaming output stores) measured best (profiles/r02_gemm_l2_hint_sweep.csv)
 int g_force_bn = 0;      // 64/128/256 = single-CTA tile width; 512 = force the 2-CTA 256x256 kernel; 0 = auto
 int g_max_ctas = 0;
 int g_group_m = 0;
@@ -1068,12 +1068,12 @@ static int gemm_dispatch(const void* A, long long lda, const void* W, long long 
   p.hint_a = p.hint_b = 0;
   p.stream_out = 0;
   if (use_2cta) {
-    if (g_l2_hints) {
-      // band of A rows (group_m x 256 rows x K) must survive the W / output streams of its raster group
-      p.hint_a = L2_EVICT_LAST;
-      p.hint_b = L2_EVICT_FIRST;
-      p.stream_out = 1;
-    }
+    // bit 0: A tiles evict_last (the band of A rows is re-read by every n-block of its raster group), bit 1: W tiles
+    // evict_first, bit 3: W tiles evict_last, bit 2: output stores with .cs (streaming) semantics
+    if (g_l2_hints & 1) p.hint_a = L2_EVICT_LAST;
+    if (g_l2_hints & 2) p.hint_b = L2_EVICT_FIRST;
+    if (g_l2_hints & 8) p.hint_b = L2_EVICT_LAST;
+    if (g_l2_hints & 4) p.stream_out = 1;
     p.group_m = g_group_m > 0 ? g_group_m : 16;    // 4096-row bands: measured +2 % over 2048 on the 7B shapes, A band + W still L2-friendly
     r = make_tensor_map(&tmB, W, N, K, ldw, 128);
     if (r) return r;
