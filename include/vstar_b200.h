@@ -27,6 +27,10 @@ extern "C" {
 
 const char* vsb_last_error(void);
 int vsb_version(void);
+/* 1: kernels are chosen independently of the number of rows in a call (no skinny-GEMM / row-RMSNorm shortcuts), so a crop's result
+ * does not depend on how many other crops share its batch - required for identical search trajectories under speculative
+ * batching and frontier sharding.  0 (default): fastest kernel per shape (decode paths). */
+int vsb_set_batch_invariant(int on);
 
 /* C[M,N] = epi(A[M,K] . W[N,K]^T + bias[N]) (+ residual[M,N]); tcgen05/TMEM/TMA GEMM, bf16 operands, fp32
  * accumulate.  out_fp32: C/residual element type (0 = bf16, 1 = fp32).  Output-row remap (rows_per_group > 0):

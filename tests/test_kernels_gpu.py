@@ -521,6 +521,31 @@ def test_owl_head_epilogues_bf16_values(ops):
     assert torch.equal(b1, b1.to(BF).float()) and float((b1 != want).float().mean()) < 1e-3 and float((b1 - b0).abs().max()) < 1.2e-2
 
 
+def test_rows_invariant_to_batch(ops):
+    """batch-invariant mode (vsb_set_batch_invariant): the first rows of a GEMM / RMSNorm are bit-identical whether the call
+    carries 3, 16, 320, 2264 or 18112 rows - i.e. the tcgen05 tile variants (32/64/128/256 wide, 2-CTA) accumulate every
+    output element in the same order, and no row-count-dependent kernel family is taken.  This is what makes a crop's record
+    independent of the batch it was evaluated in (speculative batching, frontier sharding)."""
+    torch.manual_seed(0)
+    x = (torch.randn(18112, 4096, device="cuda") * 0.5).to(BF)
+    for N, K, epi in ((4096, 4096, ops.EPI_NONE), (22016, 4096, ops.EPI_SWIGLU), (512, 4096, ops.EPI_RELU), (32004, 4096, ops.EPI_NONE)):
+        w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(BF)
+        fp32 = N == 32004
+        with ops.batch_invariant():
+            big = ops.gemm(x, w, epilogue=epi, out_dtype=torch.float32 if fp32 else BF)
+            for m in (3, 16, 17, 320, 2264):
+                y = ops.gemm(x[:m].contiguous(), w, epilogue=epi, out_dtype=torch.float32 if fp32 else BF)
+                assert torch.equal(y, big[:m]), (N, epi, m, float((y.float() - big[:m].float()).abs().max()))
+        # without the flag the skinny decode kernels take M <= 16: fast, but only equal up to bf16 rounding
+        y3 = ops.gemm(x[:3].contiguous(), w, epilogue=epi, out_dtype=torch.float32 if fp32 else BF)
+        assert rel_err(y3, big[:3]) < 2e-2
+    g = (1 + 0.1 * torch.randn(4096, device="cuda")).to(BF)
+    with ops.batch_invariant():
+        big = ops.rmsnorm(x[:4096], g, 1e-6)
+        for m in (1, 5, 32, 33):
+            assert torch.equal(ops.rmsnorm(x[:m].contiguous(), g, 1e-6), big[:m])
+
+
 def test_copy2d_and_cast(ops):
     src = rnd(50, 3 * 128, seed=90)
     dst = torch.zeros(50, 2 * 128, dtype=BF, device="cuda")

@@ -145,6 +145,30 @@ def test_pipelined_records_equal_synchronous_maps(tiny_vsm):
     assert hb.shape == (520, 700, 1) and hb.dtype == np.float32 and float(hb.max()) == 1.0 and float(hb.min()) == 0.0
 
 
+def test_crop_records_do_not_depend_on_the_batch(tiny_vsm):
+    """a crop's record is a pure function of the crop: evaluated alone, in a batch of 3 or in a batch of 8 it comes back
+    bit-identical (batch-invariant kernels) - the property that lets every rank of a sharded frontier, and every speculative
+    batch composition, walk the same trajectory"""
+    vsm, O, cfg, sd = tiny_vsm
+    img = synth_image(91, 640, 480)
+    boxes = [[0, 0, 640, 480], [0, 0, 320, 240], [320, 0, 320, 240], [0, 240, 320, 240], [320, 240, 320, 240], [160, 120, 160, 120],
+             [0, 0, 160, 120], [100, 50, 333, 222]]
+    regions = [(img, b) for b in boxes]
+    qs = ["q"] * len(boxes)
+    ss = [100] * len(boxes)
+
+    def rows(idx):
+        h = vsm.detect_regions_launch([regions[i] for i in idx], [qs[i] for i in idx], [ss[i] for i in idx], rec_len=512)
+        vsm.detect_regions_finish(h)
+        return h["rec_host"].clone()
+
+    full = rows(list(range(8)))
+    for idx in ([0], [3], [7], [1, 4, 6], [5, 2], [7, 6, 5, 4, 3, 2, 1, 0]):
+        part = rows(idx)
+        for k, i in enumerate(idx):
+            assert torch.equal(part[k], full[i]), (idx, i, float((part[k] - full[i]).abs().max()))
+
+
 def test_vsm_inference_api_modes(tiny_vsm):
     vsm, O, cfg, sd = tiny_vsm
     img = synth_image(77, 200, 150)

@@ -17,6 +17,7 @@ c_f = ctypes.c_float
 # name -> argtypes (must match include/vstar_b200.h)
 SIGNATURES = {
     "vsb_gemm_bf16": [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_p, c_p, c_ll, c_i, c_i, c_i, c_ll, c_ll, c_p],
+    "vsb_set_batch_invariant": [c_i],
     "vsb_gemm_profile_begin": [],
     "vsb_gemm_profile_end": [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_ll)],
     "vsb_gemm_set_tuning": [c_i, c_i],

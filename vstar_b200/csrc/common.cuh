@@ -12,6 +12,7 @@
 #define VSB_ERR_UNSUPPORTED -3
 
 void vsb_set_error(const char* fmt, ...);
+int vsb_batch_invariant();   // see api.cu
 
 #define VSB_CHECK_ARG(cond, ...)                 \
   do {                                           \

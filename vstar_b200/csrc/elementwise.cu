@@ -406,7 +406,7 @@ extern "C" int vsb_rmsnorm_bf16(const void* x, long long ldx, const void* w, voi
   VSB_CHECK_ARG(cols % 8 == 0 && cols <= 128 * 8 * 4 && ldx % 8 == 0 && ldy % 8 == 0, "vsb_rmsnorm_bf16: cols=%d must be a multiple of 8 and <= 4096", cols);
   if (rows <= 0) return VSB_OK;
   const int blocks = (rows + 3) / 4;
-  if (rows <= 32 && cols >= 2048 && cols <= 8192) {
+  if (rows <= 32 && cols >= 2048 && cols <= 8192 && !vsb_batch_invariant()) {
     VSB_CUDA(vsb_launch_pdl(rmsnorm_row_kernel, dim3(rows), dim3(256), 0, STREAM(stream), 1, (const bf16*)x, ldx, (const bf16*)w, (bf16*)y,
                             ldy, cols, eps));
     return VSB_OK;

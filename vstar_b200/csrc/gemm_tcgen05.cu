@@ -1020,7 +1020,7 @@ static int gemm_dispatch(const void* A, long long lda, const void* W, long long 
   // decode-sized problems are HBM-bound on W: CUDA-core streaming kernel (gemm_skinny.cu); force_bn = 1 forces it (tests)
   // measured (tools/bench_vqa.py, CUDA-graph timing, fraction of the HBM roofline): FMA kernel 0.57-0.96 at M = 1; mma.sync
   // kernel 0.44-0.79 for M = 2..8 (and ahead of the tcgen05 tiles on N <= 8192 up to M = 16); tcgen05 tiles 0.26-0.76 at M = 16
-  if ((K % 8) == 0) {
+  if ((K % 8) == 0 && !(vsb_batch_invariant() && g_force_bn == 0)) {
     int variant = 0;
     if (g_force_bn == 1 && M <= 8) variant = 1;
     else if (g_force_bn == 2 && M <= 16) variant = 2;

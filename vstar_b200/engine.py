@@ -478,6 +478,10 @@ class VSMEngine(LlamaClipCore):
     def model_forward(self, images, images_clip, input_ids, mode="detection"):
         """Teacher-forced single pass == VSMForCausalLM.model_forward(inference=True) (VSM.py:201-364), batched over B.
         input_ids [B,L] already contain the answer.  Returns dict of device tensors."""
+        with ops.batch_invariant():
+            return self._model_forward(images, images_clip, input_ids, mode)
+
+    def _model_forward(self, images, images_clip, input_ids, mode):
         c = self.cfg
         B, L = input_ids.shape
         x, T, img_pos = self.prefill(input_ids, images_clip)
@@ -526,7 +530,13 @@ class VSMEngine(LlamaClipCore):
         """== VSMForCausalLM.inference (VSM.py:438-553) for a batch of crops sharing one prompt length.
         prompt_ids [B,Lp]; draft_ids [g] = the expected greedy answer incl. EOS (e.g. tokenizer("Sure, [LOC] .")+EOS).
         `forced_ids` (tests / synthetic weights only) forces the emitted tokens like a logits processor would, in which
-        case verification compares nothing and the draft is taken as the answer."""
+        case verification compares nothing and the draft is taken as the answer.
+
+        Runs in batch-invariant mode (ops.batch_invariant): a crop's outputs do not depend on the size of its batch."""
+        with ops.batch_invariant():
+            return self._inference(images, images_clip, prompt_ids, draft_ids, eos_token_id, max_new_tokens, mode, forced_ids, defer)
+
+    def _inference(self, images, images_clip, prompt_ids, draft_ids, eos_token_id, max_new_tokens, mode, forced_ids, defer):
         c = self.cfg
         B, Lp = prompt_ids.shape
         g = len(draft_ids)

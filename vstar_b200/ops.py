@@ -35,6 +35,21 @@ def _rows2d(t):
     return t.data_ptr(), t.shape[0], t.shape[1], t.stride(0)
 
 
+class batch_invariant:
+    """with ops.batch_invariant(): kernels are chosen independently of the row count of a call (see vsb_set_batch_invariant)"""
+    depth = 0
+
+    def __enter__(self):
+        if batch_invariant.depth == 0:
+            call("vsb_set_batch_invariant", 1)
+        batch_invariant.depth += 1
+
+    def __exit__(self, *a):
+        batch_invariant.depth -= 1
+        if batch_invariant.depth == 0:
+            call("vsb_set_batch_invariant", 0)
+
+
 # optional per-launch profiling of the dominant kernel (bench.py roofline): CUDA events around every GEMM launch
 def profile_begin():
     """CUDA events around every vsb_gemm_bf16 launch from here on (recorded inside the library, so launches issued by the native
