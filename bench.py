@@ -344,7 +344,17 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner to STDOUT when the first communicator comes up; keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     from vstar_b200 import _lib, ops, seal, synth
     from vstar_b200.config import VSMConfig, tiny_config
@@ -574,14 +584,16 @@ def run_b200(args):
             f_images = images_for(fs_n, f_side, 9000)                   # the SAME images on every rank (SPMD controller)
             f_jobs = [(im, TARGETS[0], f_small) for im in f_images]
             front = ShardedVSM(vsm, device="cuda") if world > 1 else vsm
+            # scheduling only (the work is the same for every N): keep >= 32 crops per rank in a full frontier batch
+            f_batch = max(args.batch, 32 * world)
 
             def fstep():
                 vsm.release()
-                return visual_search_many(front, f_jobs, batch_size=args.batch, depth=args.depth, **kw)
+                return visual_search_many(front, f_jobs, batch_size=f_batch, depth=args.depth, **kw)
 
             # parity first: the sharded trajectories against this rank's own single-GPU run of the same searches
             vsm.release()
-            _, ref_states = visual_search_many(vsm, f_jobs, batch_size=args.batch, depth=args.depth, **kw)
+            _, ref_states = visual_search_many(vsm, f_jobs, batch_size=args.batch, depth=args.depth, **kw)       # single-GPU schedule
             _, sh_states = fstep()
             ref_traj = [[tuple(s["bbox"]) for s in st.search_path] for st in ref_states]
             sh_traj = [[tuple(s["bbox"]) for s in st.search_path] for st in sh_states]
@@ -626,7 +638,7 @@ def run_b200(args):
             rounds = max(1, (g1[1] - g0[1]) // (n_f + 1))
             out["frontier"] = {
                 "workload": f"BASELINE.json configs[3]-shaped: {fs_n} searches of {f_side}x{f_side} images, smallest {f_small} "
-                            f"({crops_f // n_f // fs_n} crops each), ONE controller, every frontier batch (<= {args.batch} crops) dealt "
+                            f"({crops_f // n_f // fs_n} crops each), ONE controller, every frontier batch (<= {f_batch} crops) dealt "
                             f"round-robin over all {world} ranks; total work is the same for every N",
                 "scaling": "strong", "value": crops_f / (ms_f / 1e3), "unit": "crops/s", "steps": n_f, "ms_per_step": ms_f / n_f,
                 "collective": ("ncclAllGather (all_gather_into_tensor) of fixed-size crop records, one per frontier batch" if world > 1
