@@ -227,3 +227,32 @@ def test_vsmforcausallm_mirror_api(tiny_vsm):
     oid2, pm2, det2 = m.inference(ic, io, prompt.cuda(), [(768, 768)], [(120, 160)], max_new_tokens=6, mode="detection")
     if cfg.loc_token_idx not in oid[0].tolist():
         assert pm2 == [] and det2 is None
+
+
+def test_cuda_graph_replay_equals_eager(tiny_vsm):
+    """small frontier batches run as captured CUDA graphs after two eager calls of the same shape: records from the replays are
+    bit-identical to the eager ones, for changing images / boxes, and the eager path takes over again when graphs are disabled"""
+    vsm, O, cfg, sd = tiny_vsm
+    eng = vsm.engine
+    imgs = [synth_image(300 + k, 500 + 20 * k, 400 + 10 * k) for k in range(6)]
+    regions = [[(imgs[k], [10 * k, 5 * k, 300 + k, 250 - k]), (imgs[k], [0, 0, imgs[k].width, imgs[k].height])] for k in range(6)]
+
+    def rows(rg):
+        h = vsm.detect_regions_launch(rg, ["q"] * len(rg), [100] * len(rg), rec_len=512)
+        vsm.detect_regions_finish(h)
+        return h["rec_host"].clone()
+
+    saved = eng.graph_max_batch
+    try:
+        eng.graph_max_batch = 0
+        eng._graphs.clear(); eng._graph_seen.clear()
+        eager = [rows(rg) for rg in regions]
+        eng.graph_max_batch = 8
+        r0 = eng.stats.get("graph_replays", 0)
+        graphed = [rows(rg) for rg in regions]
+        assert eng.stats.get("graph_capture_errors", 0) == 0, getattr(eng, "last_graph_error", None)
+        assert eng.stats.get("graph_replays", 0) - r0 >= 3          # calls 3.. of the shape replay the graph
+        for a, b in zip(eager, graphed):
+            assert torch.equal(a, b), float((a - b).abs().max())
+    finally:
+        eng.graph_max_batch = saved

@@ -216,6 +216,25 @@ class LlamaClipCore:
         self._prefix_slots = 0           # cache slots whose rows 0..P currently hold it
         self._P = 0                      # prefix rows omitted from the residual stream returned by the last prefill
         self._Tn = 0
+        self._consts = {}                # small index tensors on the device, built once per shape (also keeps graph capture clean)
+        # CUDA graphs for small frontier batches (VSMEngine.inference): a single crop is ~1400 kernels of a few microseconds,
+        # i.e. bound by the host's launch rate, not by the GPU; replaying one captured graph removes that
+        self.graph_max_batch = int(os.environ.get("VSB_GRAPH_MAX_BATCH", "8"))
+        self._graphs = {}
+        self._graph_seen = {}
+        self._capturing = False
+
+    def _const(self, key, values, dtype=torch.int64):
+        """device tensor of a small host list, cached by key (pure function of the call's shape parameters)"""
+        t = self._consts.get(key)
+        if t is None:
+            if self._capturing:
+                raise RuntimeError(f"device constant {key!r} requested for the first time during graph capture")
+            if len(self._consts) > 512:
+                self._consts.clear()
+            t = torch.tensor(values, dtype=dtype).to(self.dev)
+            self._consts[key] = t
+        return t
 
     # ------------------------------------------------------------------ ViT
     def _vit_forward(self, vw, pixels, patch, heads, image, eps):
@@ -277,6 +296,8 @@ class LlamaClipCore:
             self._cache[:, :cur[1], :cur[2]].copy_(old)
         self._cache_shape = shape
         self._prefix_slots = 0
+        self._graphs.clear()            # captured graphs hold pointers into the old cache
+        self._graph_seen.clear()
         return self._cache
 
     def _llm_layers(self, x, B, Tn, past, Tmax, positions=None, k_start=None, cache_row_offset=0, tail_rows=0, q_seg=None, seg_lo=0):
@@ -307,7 +328,7 @@ class LlamaClipCore:
         assert pos >= self._P, "position inside the shared prefix: its rows are not recomputed"
         return b * self._Tn + pos - self._P
 
-    def prefill(self, input_ids, images_clip, tail_rows=0, reserve=0):
+    def prefill(self, input_ids, images_clip, tail_rows=0, reserve=0, ids_dev=None):
         """input_ids int64 [B, L] (same L and same image position for the whole batch), images_clip [B,3,224,224] bf16.
         tail_rows > 0: the caller reads only the last tail_rows positions of every crop (see vsb_llama_layers).
         reserve: positions the caller will append by decoding (the cache slot is sized for T + reserve up front).
@@ -349,10 +370,12 @@ class LlamaClipCore:
         # input buffer: patch row i of crop b -> x[b*Tn + img_pos - P + i].  The CLS row lands on the <im_start> slot
         # (img_pos - 1 >= P) and is overwritten by the embedding splice below.
         ops.gemm(ct, self.w.mm_w, out=x, bias=self.w.mm_b, rows_per_group=S, group_stride=Tn, group_offset=img_pos - 1 - P)
-        ids_new = (input_ids[:, P:] if P else input_ids).contiguous().to(self.dev, non_blocking=True)
+        # ids_dev: the caller already holds input_ids[:, P:] on the device (static buffer of a captured graph)
+        ids_new = ids_dev if ids_dev is not None else (input_ids[:, P:] if P else input_ids).contiguous().to(self.dev, non_blocking=True)
         ops.embed_splice(ids_new, self.w.embed, x, img_pos - P, n_img)
         if P:
             if self._prefix_slots < B:                  # slots that do not hold the prefix rows yet
+                assert not self._capturing, "prefix rows must be in place before a graph is captured"
                 self._cache[:, self._prefix_slots:B, :P].copy_(self._prefix_kv[:, None])
                 self._prefix_slots = B
             self.stats["prefix_shared"] += B
@@ -410,7 +433,7 @@ class VSMEngine(LlamaClipCore):
         B = fmap.shape[0] // P
         img = ops.gemm(fmap, w.vp_w, bias=w.no_mask)                  # visual_projection + no_mask_embed (dense prompt)
         if crop_of_loc != list(range(B)):
-            idx = torch.tensor(crop_of_loc, device=self.dev)
+            idx = self._const(("col", tuple(crop_of_loc)), crop_of_loc)
             img = img.view(B, P, D).index_select(0, idx).reshape(n * P, D).contiguous()
         keys = img
         tokens = torch.empty((n, 6, D), dtype=BF, device=self.dev)
@@ -469,7 +492,7 @@ class VSMEngine(LlamaClipCore):
         if crop_of_loc == list(range(B)):
             logits, scores = ops.owl_class_post(y, det_q.contiguous(), P, Q, quant_bf16=self.heads_bf16)
             return logits.view(n, P), scores.view(n, P), boxes          # one entry per crop: boxes [n,P,4] with n == B
-        idx = torch.tensor(crop_of_loc, device=self.dev)
+        idx = self._const(("col", tuple(crop_of_loc)), crop_of_loc)
         yy = y.view(B, P, Q + 2).index_select(0, idx).reshape(n * P, Q + 2).contiguous()
         logits, scores = ops.owl_class_post(yy, det_q.contiguous(), P, Q, quant_bf16=self.heads_bf16)
         return logits.view(n, P), scores.view(n, P), boxes.index_select(0, idx)
@@ -500,7 +523,7 @@ class VSMEngine(LlamaClipCore):
 
     def _heads(self, x, T, rows, crop_of_loc, images, mode):
         c = self.cfg
-        rows_t = torch.tensor(rows, dtype=torch.int64, device=self.dev)
+        rows_t = self._const(("rows", tuple(rows)), rows)
         sel = ops.gather_rows(rows_t, x)
         hn = ops.rmsnorm(sel, self.w.final_norm, c.rms_eps)
         seg_q = self._mlp2(hn, self.w.fcs["seg"])
@@ -542,23 +565,36 @@ class VSMEngine(LlamaClipCore):
         g = len(draft_ids)
         draft = torch.as_tensor(draft_ids, dtype=torch.int64)
         ids = torch.cat([prompt_ids.cpu(), draft[:-1].unsqueeze(0).expand(B, -1)], dim=1).contiguous()      # host tensor
-        x, T, img_pos = self.prefill(ids, images_clip, tail_rows=g)      # only the g answer-predicting rows are read below
-        n_img = c.clip_tokens
-        # rows that predict answer token j (j = 0..g-1): original index Lp-1+j -> spliced row +255
-        pred_rows = torch.tensor([self.x_row(b, (Lp - 1 + j) + n_img - 1) for b in range(B) for j in range(g)], dtype=torch.int64, device=self.dev)
-        hn, am, logits = self._logits_rows(x, pred_rows)
-        self.last_logits = logits.view(B, g, -1)
+        key = self._graph_key(ids, B, Lp, draft_ids, mode) if defer else None
+        if key is not None:
+            dev = self._graph_run(key, images, images_clip, ids, Lp, g, mode)
+        else:
+            dev = self._crop_forward(images, images_clip, ids, None, Lp, g, mode)
         d_host = torch.as_tensor(draft_ids, dtype=torch.int64)
         out_ids = [torch.cat([prompt_ids[b].cpu(), d_host]) for b in range(B)]
         # crops whose greedy answer deviates from the draft are flagged (finish()); the caller re-runs them with exact
         # step-wise greedy decoding (VSMEngine.generate) so emitted ids are always the reference's greedy ids.  With
         # defer=True nothing here waits for the GPU: the caller can prepare the next chunk while this one runs.
-        pending = dict(verified=None, _am=am, _draft=d_host, _forced=forced_ids is not None, n_crops=B)
+        out = dict(dev)
+        out.update(verified=None, _draft=d_host, _forced=forced_ids is not None, n_crops=B, output_ids=out_ids)
+        return out if defer else self.finish(out)
+
+    def _crop_forward(self, images, images_clip, ids, ids_dev, Lp, g, mode):
+        """device work of one draft-verified batch: prefill over prompt + draft, logits of the g answer-predicting rows, heads.
+        No host synchronisation and (once the shape has been seen) no host->device traffic: this is what a CUDA graph captures."""
+        c = self.cfg
+        B = ids.shape[0]
+        x, T, img_pos = self.prefill(ids, images_clip, tail_rows=g, ids_dev=ids_dev)     # only the g answer-predicting rows are read below
+        n_img = c.clip_tokens
+        # rows that predict answer token j (j = 0..g-1): original index Lp-1+j -> spliced row +255
+        pr = [self.x_row(b, (Lp - 1 + j) + n_img - 1) for b in range(B) for j in range(g)]
+        hn, am, logits = self._logits_rows(x, self._const(("rows", tuple(pr)), pr))
+        self.last_logits = logits.view(B, g, -1)
+        out = dict(_am=am)
         if mode == "vqa":
-            pending["output_ids"] = out_ids
-            return pending if defer else self.finish(pending)
+            return out
         rows, crop_of_loc = [], []
-        d_cpu = d_host.tolist()
+        d_cpu = ids[0, Lp:].tolist() + [None]                 # draft[:-1] is in ids; the last draft token (EOS) predicts nothing
         for b in range(B):
             for j, tok in enumerate(d_cpu):
                 if tok == c.loc_token_idx:
@@ -566,10 +602,91 @@ class VSMEngine(LlamaClipCore):
                     crop_of_loc.append(b)
         if not rows:
             raise RuntimeError("no [LOC] token generated (reference: IndexError at visual_search.py:209-211)")
-        out = self._heads(x, T, rows, crop_of_loc, images, mode)
-        out["output_ids"] = out_ids
-        out.update(pending)
-        return out if defer else self.finish(out)
+        out.update(self._heads(x, T, rows, crop_of_loc, images, mode))
+        return out
+
+    # ------------------------------------------------------------------ CUDA graphs for small frontier batches
+    def _graph_key(self, ids, B, Lp, draft_ids, mode):
+        """hashable shape key if this call can run as a captured graph: small batch, one <image>, the shared prefix already
+        snapshotted and in use (steady state of a search), cache large enough"""
+        if self.graph_max_batch <= 0 or B > self.graph_max_batch or self._capturing or not self.prefix_cache or self._prefix_ids is None \
+                or ops.profiling:                 # (per-launch GEMM events of bench.py's roofline leg cannot be recorded inside a graph)
+            return None
+        pos = (ids[0] == IMAGE_TOKEN_INDEX).nonzero()
+        if pos.numel() != 1:
+            return None
+        img_pos = int(pos[0, 0])
+        P = len(self._prefix_ids)
+        if img_pos - 1 != P or not bool((ids[:, :P] == torch.tensor(self._prefix_ids)).all()) or not bool((ids[:, img_pos] == IMAGE_TOKEN_INDEX).all()):
+            return None
+        return (B, Lp, img_pos, tuple(int(t) for t in draft_ids), mode, self.heads_bf16, self.tail_only)
+
+    def _graph_run(self, key, images, images_clip, ids, Lp, g, mode):
+        from . import _lib
+        ent = self._graphs.get(key)
+        B = ids.shape[0]
+        P = len(self._prefix_ids)
+        if ent is None:
+            n = self._graph_seen.get(key, 0) + 1
+            self._graph_seen[key] = n
+            if n <= 2:                                        # eager warm-up: kernel attributes, device constants, cache, prefix rows
+                return self._crop_forward(images, images_clip, ids, None, Lp, g, mode)
+            ent = self._graph_capture(key, images, images_clip, ids, Lp, g, mode)
+        if ent is False:                                      # capture failed once: stay eager for this shape
+            return self._crop_forward(images, images_clip, ids, None, Lp, g, mode)
+        ent["images"].copy_(images, non_blocking=True)
+        ent["images_clip"].copy_(images_clip, non_blocking=True)
+        ent["ids"].copy_(ids[:, P:], non_blocking=True)
+        if self._prefix_slots < B:                            # slots that lost / never had the prefix rows
+            self._cache[:, self._prefix_slots:B, :P].copy_(self._prefix_kv[:, None])
+            self._prefix_slots = B
+        ent["graph"].replay()
+        _lib.launches += ent["launches"]
+        self.stats["prefix_shared"] += B
+        self.stats["graph_replays"] = self.stats.get("graph_replays", 0) + 1
+        self._P, self._Tn = ent["P"], ent["Tn"]
+        # the graph's output buffers are overwritten by its next replay: hand out copies of what callers keep
+        out = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in ent["out"].items()}
+        self.last_logits = None
+        return out
+
+    def _graph_capture(self, key, images, images_clip, ids, Lp, g, mode):
+        from . import _lib
+        B = ids.shape[0]
+        P = len(self._prefix_ids)
+        if len(self._graphs) >= 16:
+            self._graphs.pop(next(iter(self._graphs)))
+        try:
+            st_images, st_clip = torch.empty_like(images), torch.empty_like(images_clip)
+            st_ids = ids[:, P:].contiguous().to(self.dev)
+            st_images.copy_(images)
+            st_clip.copy_(images_clip)
+            if self._prefix_slots < B:
+                self._cache[:, self._prefix_slots:B, :P].copy_(self._prefix_kv[:, None])
+                self._prefix_slots = B
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            l0 = _lib.launches
+            shared0 = self.stats["prefix_shared"]
+            self._capturing = True
+            try:
+                with torch.cuda.graph(graph):
+                    out = self._crop_forward(st_images, st_clip, ids, st_ids, Lp, g, mode)
+            finally:
+                self._capturing = False
+            self.stats["prefix_shared"] = shared0
+            keep = ("_am", "low_res_masks", "pred_logits", "scores", "pred_boxes", "crop_of_loc")
+            ent = dict(graph=graph, images=st_images, images_clip=st_clip, ids=st_ids, launches=_lib.launches - l0, P=self._P, Tn=self._Tn,
+                       out={k: v for k, v in out.items() if k in keep})
+            _lib.launches = l0
+            self.stats["graphs_captured"] = self.stats.get("graphs_captured", 0) + 1
+        except Exception as e:          # never let a capture problem break the search: this shape stays on the eager path
+            self._capturing = False
+            self.stats["graph_capture_errors"] = self.stats.get("graph_capture_errors", 0) + 1
+            self.last_graph_error = repr(e)
+            ent = False
+        self._graphs[key] = ent
+        return ent
 
     def generate(self, prompt_ids, images_clip, max_new_tokens=100, eos_token_id=2, forced_ids=None):
         """Exact greedy decoding for ONE sequence on the fused-QKV cache (reference: HF generate, use_cache=False —

@@ -51,17 +51,24 @@ class batch_invariant:
 
 
 # optional per-launch profiling of the dominant kernel (bench.py roofline): CUDA events around every GEMM launch
+profiling = False
+
+
 def profile_begin():
     """CUDA events around every vsb_gemm_bf16 launch from here on (recorded inside the library, so launches issued by the native
     layer runner are covered too)"""
+    global profiling
+    profiling = True
     call("vsb_gemm_profile_begin")
 
 
 def profile_end():
     """-> (total algorithmic flops, total ms, launches) over the GEMM launches since profile_begin()"""
     import ctypes
+    global profiling
     f, t, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
     call("vsb_gemm_profile_end", ctypes.byref(f), ctypes.byref(t), ctypes.byref(n))
+    profiling = False
     return f.value, t.value, n.value
 
 
