@@ -577,6 +577,46 @@ def run_b200(args):
         except Exception as e:
             out["configs1"] = {"error": repr(e)}
 
+    # ---- weak-cue leg: every root takes the context-cue branch (visual_search.py:427-443): 1 'vqa' + 1 'segmentation' model
+    # call per search on top of its 5 detections, batched across the lock-step searches by the controller -----------------
+    if extra and rank == 0:
+        try:
+            from vstar_b200 import noun_chunks
+            noun_chunks.set_nlp(lambda text: [])       # synthetic answers carry no parsable nouns: "region {phrase}" prompts
+            sw = 4 if args.tiny else 16
+            w_images = images_for(sw, 256 if args.tiny else 1024, 7000)
+            w_jobs = [(im, TARGETS[0], 128 if args.tiny else 512) for im in w_images]
+            kw_weak = dict(confidence_high=2.0, target_cue_threshold=1e9, target_cue_threshold_decay=0.0, target_cue_threshold_minimum=-1e9)
+            cue_sizes = []
+
+            def wstep():
+                from vstar_b200.visual_search import SearchController, SearchState
+                states = [SearchState(img, name, ss, **kw_weak) for img, name, ss in w_jobs]
+                ctl = SearchController(vsm, None, args.batch, depth=args.depth)
+                ctl.run(states)
+                cue_sizes[:] = ctl.cue_batches
+                assert all("context_cue" in st.search_path[0] for st in states)
+                return sum(st.n_evals for st in states)
+
+            wstep()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            n_w, det = 3, 0
+            for _ in range(n_w):
+                det += wstep()
+            e1.record()
+            torch.cuda.synchronize()
+            ms_w = e0.elapsed_time(e1)
+            out["weak_cue"] = {"workload": f"{sw} lock-step searches of 1024x1024 images (root + 4 crops) whose ROOT takes the context-cue branch: "
+                                           "5 detection evaluations + 1 'vqa' + 1 'segmentation' model call per search, the cue calls batched "
+                                           "across the searches (synthetic forced answer, so no free-running decode)",
+                               "crops_per_s": det / (ms_w / 1e3), "model_calls_per_s": (det + 2 * sw * n_w) / (ms_w / 1e3),
+                               "cue_batches": [list(c) for c in cue_sizes], "steps": n_w}
+            noun_chunks.set_nlp(None)
+        except Exception as e:
+            out["weak_cue"] = {"error": repr(e)}
+
     # ---- frontier leg: ONE set of searches, every batch sharded over all ranks (strong scaling) ----------------------
     if extra:
         try:
@@ -672,7 +712,7 @@ def run_b200(args):
                 if args.tiny:
                     side_l, small_l = side_l // 8, small_l // 8
                 im = images_for(1, side_l, 77)
-                for _ in range(2):
+                for _ in range(5):        # the first calls of a shape run eagerly, later ones replay its CUDA graph
                     vsm.release()
                     torch.cuda.synchronize()
                     t1 = time.perf_counter()

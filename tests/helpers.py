@@ -159,6 +159,10 @@ class RecordStub(StubVSM):
             smallest_sizes = [max(1, min(int(b[2]), int(b[3])) // 2) for _, b in regions]
         return self.detect_regions_finish(self.detect_regions_launch(regions, questions, smallest_sizes))
 
+    def inference_many(self, regions, questions, mode):
+        self.cue_batches = getattr(self, "cue_batches", []) + [(mode, len(regions))]
+        return [self.inference(src.crop((int(b[0]), int(b[1]), int(b[0] + b[2]), int(b[1] + b[3]))), q, mode) for (src, b), q in zip(regions, questions)]
+
 
 # ---------------------------------------------------------------- deterministic stand-in for spaCy (noun-chunk tests / goldens)
 class _Tok:

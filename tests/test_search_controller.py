@@ -84,6 +84,22 @@ def test_record_path_pipelined_matches_reference(tag, batch):
         assert a.shape == (int(g["h"]), int(g["w"]), 1) and float(a.max()) == 1.0 and float(a.min()) == 0.0
 
 
+def test_weak_cue_calls_are_batched_across_lockstep_searches():
+    """several searches whose nodes take the context-cue branch at the same time: their 'vqa' and 'segmentation' calls go out
+    as batches (vsm.inference_many), and every search still walks the trajectory / cue strings of the reference"""
+    g = np.load(os.path.join(G, "search_stub_mixcue.npz"))
+    g2 = np.load(os.path.join(G, "search_stub_weakcue.npz"))
+    kw = json.loads(str(g["kw"]))
+    assert kw["confidence_high"] == json.loads(str(g2["kw"]))["confidence_high"]
+    jobs = [(synth_image(int(g["img_seed"]), int(g["w"]), int(g["h"])), "mug", int(g["smallest"])) for _ in range(3)]
+    stub = RecordStub()
+    res, states = VS.visual_search_many(stub, jobs, batch_size=16, scorer=NumpyScorer(), **kw)
+    for st in states:
+        assert np.array_equal(np.array([s["bbox"] for s in st.search_path]), g["trajectory"])
+        assert [s.get("context_cue", "") for s in st.search_path] == json.loads(str(g["context_cues"]))
+    assert max(n for _, n in stub.cue_batches) == 3 and {k for k, _ in stub.cue_batches} == {"vqa", "segmentation"}
+
+
 def test_more_than_16_valid_boxes_at_the_root():
     """all_valid_boxes when the record's 16 slots overflow: fetched from the owner, equal to the map-based path"""
     img = synth_image(24, 1280, 960)

@@ -66,7 +66,8 @@ def tiny_vsm():
 def test_model_search_trajectory_vs_reference_golden(tiny_vsm, tag):
     """reference model x reference search loop (fp32, CPU, oracle/make_golden.py) vs the bf16 engine inside the product
     controller (crop records, pipelined batches).  Order must be IDENTICAL whenever the reference's closest pair of queue
-    priorities is further apart than the bf16 score tolerance; inside a near-tie an inversion is allowed (and reported)."""
+    priorities is further apart than twice the measured score error; a pair may swap only if its reference gap is below that
+    (with the tiny random-weight golden model the heat maps are nearly flat, so such near-ties exist; they are reported)."""
     from vstar_b200 import visual_search as VS
     vsm, O, cfg, sd = tiny_vsm
     g = np.load(os.path.join(G, f"search_model_{tag}.npz"))
@@ -98,7 +99,7 @@ def test_model_search_trajectory_vs_reference_golden(tiny_vsm, tag):
     PARITY[f"search_model_{tag}"] = dict(nodes=len(ref), identical_order=same, min_ref_priority_gap=min_gap, max_score_err=max_score_err,
                                          worst_inverted_gap=worst, tol=TOL, batches=None)
     assert max_score_err < TOL
-    assert worst < TOL, worst
+    assert worst <= 2 * max_score_err + 1e-7, (worst, max_score_err)      # two scores off by e in opposite directions can swap a 2e gap
     if min_gap > 2 * max_score_err:
         assert same, "priorities are separated by more than the score error, so the expansion order must be the reference's"
     if same:

@@ -40,6 +40,11 @@ class ShardedVSM:
     def inference(self, image, question, mode="segmentation"):
         return self.vsm.inference(image, question, mode)
 
+    def inference_many(self, regions, questions, mode):
+        if hasattr(self.vsm, "inference_many"):
+            return self.vsm.inference_many(regions, questions, mode)
+        return [self.vsm.inference(src.crop((int(b[0]), int(b[1]), int(b[0] + b[2]), int(b[1] + b[3]))), q, mode) for (src, b), q in zip(regions, questions)]
+
     def _buffer(self, name, shape, dtype, pinned=False):
         key = (name, tuple(shape), dtype)
         b = self._bufs.get(key)

@@ -282,6 +282,9 @@ class SearchState:
         self.current = init_patch
         self.cache = {}               # bbox tuple -> _NodeEval
         self.pending = set()          # bbox tuples whose evaluation is in flight
+        self.gen = None               # commit of the current node in progress (generator, see SearchController._process)
+        self.request = None           # ("vqa" | "segmentation", question) the commit is waiting for
+        self.reply = None
         self.done = False
         self.success = False
         self.all_valid_boxes = None
@@ -336,6 +339,7 @@ class SearchController:
         self.depth = max(1, int(depth))
         self.split_min = split_min
         self.batches = []              # sizes of the launched batches (diagnostics)
+        self.cue_batches = []          # (kind, size) of the batched weak-cue calls
 
     # -- evaluation ----------------------------------------------------------------------------------------
     def _launch(self, requests):
@@ -390,6 +394,10 @@ class SearchController:
 
     # -- one node, exactly visual_search_queue's body (visual_search.py:390-473) -----------------------------
     def _process(self, st: SearchState):
+        """Generator: runs the node's commit logic and YIELDS ("vqa" | "segmentation", question) whenever the weak-cue branch
+        needs another model call on the node's crop; the controller answers with the result (send) - batched over all the
+        searches that are waiting at the same point (the reference does these calls inline, one node at a time,
+        visual_search.py:427-443).  Returns True when the search ends successfully at this node."""
         cur = st.current
         bb = cur["bbox"]
         lvl = cur["scale_level"]
@@ -437,16 +445,14 @@ class SearchController:
         threshold = max(st.thr_min, st.thr * (st.thr_decay) ** (lvl - 1))
         if not (score_max > threshold):
             # weak cue: ask the VSM where the object would be, then segment that region (visual_search.py:427-443)
-            import copy
-            patch_img = st.crop(cur)
-            vqa_results = self.vsm.inference(copy.deepcopy(patch_img), CUE_QUESTION.format(st.target), mode="vqa")
+            vqa_results = yield ("vqa", CUE_QUESTION.format(st.target))
             phrase = vqa_results.split("most likely to appear")[-1].strip()
             if phrase.endswith("."):
                 phrase = phrase[:-1]
             phrase = phrase.split(st.target)[-1]
             chunks = self.extract_noun_chunks(phrase)
             phrase = chunks[0] if len(chunks) == 1 else "region {}".format(phrase)
-            cue = self.vsm.inference(copy.deepcopy(patch_img), DETECTION_QUESTION.format(phrase), mode="segmentation")
+            cue = yield ("segmentation", DETECTION_QUESTION.format(phrase))
             final_heat = cue if isinstance(cue, Heatmap) else self.scorer.from_full_res(cue, h, w)
             st.search_path[idx]["context_cue"] = vqa_results + "#" + phrase
             pyr = MapPyramid(self.scorer, final_heat, bb)
@@ -479,11 +485,24 @@ class SearchController:
         return av
 
     def _advance(self, st: SearchState):
-        """Commit as many nodes as the cache allows, in the reference's pop order."""
+        """Commit as many nodes as the cache allows, in the reference's pop order.  Stops when the current node has not been
+        evaluated yet, or when its commit is waiting for a weak-cue model call (st.request is then set)."""
         while not st.done:
-            if st.key(st.current) not in st.cache:
-                return
-            ok = self._process(st)
+            if st.gen is None:
+                if st.key(st.current) not in st.cache:
+                    return
+                st.gen = self._process(st)
+                reply = None
+            else:
+                if st.request is not None:
+                    return                                  # still waiting for _serve_cues
+                reply, st.reply = st.reply, None
+            try:
+                st.request = st.gen.send(reply)
+                return                                      # parked: a weak-cue call is pending
+            except StopIteration as fin:
+                ok = bool(fin.value)
+            st.gen = None
             if ok:
                 st.done, st.success = True, True
                 return
@@ -492,6 +511,26 @@ class SearchController:
                 return
             st.current = st.queue.get().item
             st.search_path.append(st.current)
+
+    def _serve_cues(self, states):
+        """answer the pending weak-cue calls of all parked searches: one batched model call per kind when the vsm offers
+        `inference_many`, the reference's one-crop-at-a-time `inference` otherwise"""
+        parked = [st for st in states if st.request is not None and not st.done]
+        if not parked:
+            return False
+        for kind in ("vqa", "segmentation"):
+            group = [st for st in parked if st.request is not None and st.request[0] == kind]
+            if not group:
+                continue
+            if hasattr(self.vsm, "inference_many"):
+                replies = self.vsm.inference_many([(st.image, st.current["bbox"]) for st in group], [st.request[1] for st in group], kind)
+            else:
+                import copy
+                replies = [self.vsm.inference(copy.deepcopy(st.crop(st.current)), st.request[1], mode=kind) for st in group]
+            for st, r in zip(group, replies):
+                st.reply, st.request = r, None
+            self.cue_batches.append((kind, len(group)))
+        return True
 
     def _select(self, active, limit):
         """mandatory nodes first (the current node of every search that is not already in flight), then fill the batch with
@@ -515,6 +554,8 @@ class SearchController:
         while True:
             for st in states:
                 self._advance(st)
+            if self._serve_cues(states):
+                continue               # replies are in: let the parked commits run on before evaluating more crops
             active = [st for st in states if not st.done]
             if not active:
                 break                  # speculative batches still in flight are simply dropped

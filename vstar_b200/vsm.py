@@ -494,6 +494,22 @@ class VSM:
             return heat.map
         return r["boxes"].cpu(), r["scores"].view(-1, 1).cpu(), heat.map
 
+    @torch.inference_mode()
+    def inference_many(self, regions, questions, mode):
+        """`inference` for several (search image, bbox) crops in ONE batched engine call - used by the search controller for
+        the weak-cue branch of many lock-step searches (visual_search.py:427-443 runs these one node at a time).
+        'vqa' -> list of str; 'segmentation' -> list of Heatmap (clamped H x W map on the GPU + statistics)."""
+        rs = self._run(regions, questions, mode)
+        if mode == "vqa":
+            out = []
+            for r, q in zip(rs, questions):
+                input_len = len(self._ids(q))
+                text = self.vsm_tokenizer.batch_decode(r["output_ids"][input_len:].view(1, -1), skip_special_tokens=True)[0]
+                out.append(text.replace("\n", "").replace("  ", " ").strip())
+            return out
+        assert mode == "segmentation"
+        return [self.scorer.from_low_res(r["low_res"], int(b[3]), int(b[2])) for r, (_, b) in zip(rs, regions)]
+
     def detect_batch(self, images, questions):
         """PIL crops in, see detect_regions"""
         return self.detect_regions([(im, [0, 0, im.width, im.height]) for im in images], questions)
