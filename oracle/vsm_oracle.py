@@ -413,8 +413,8 @@ def model_forward_inference(sd, cfg, images, images_clip, input_ids, original_si
     """VSMForCausalLM.model_forward(inference=True) (VSM.py:201-364): teacher-forced
     single pass; `input_ids` already contains the answer with [LOC]."""
     m = input_ids[:, 1:] == cfg.loc_token_idx
-    m = torch.cat([m, torch.zeros((m.shape[0], 1), dtype=torch.bool)], dim=1)
-    loc_mask = torch.cat([torch.zeros((m.shape[0], 255), dtype=torch.bool), m], dim=1)
+    m = torch.cat([m, torch.zeros((m.shape[0], 1), dtype=torch.bool, device=m.device)], dim=1)
+    loc_mask = torch.cat([torch.zeros((m.shape[0], 255), dtype=torch.bool, device=m.device), m], dim=1)
     logits, hidden = lm_forward(sd, cfg, input_ids, images_clip)
     out = vsm_heads(sd, cfg, hidden, loc_mask, images, original_size)
     out["hidden"], out["logits"] = hidden, logits
