@@ -91,6 +91,11 @@ def _bcast_worker(rank, world, port, q):
     load = broadcast_loader(get, src=0, device="cpu")
     got = {n: load(n) for n in names}
     ok = all(torch.equal(got[n], synth.synthetic_tensor(n, shapes[n], seed=77)) for n in names)
+    # with an index known on rank 0 (safetensors header / shape table) it is broadcast once and tensors travel without metadata
+    idx = {n: (tuple(shapes[n]), torch.float32) for n in names} if rank == 0 else None
+    load2 = broadcast_loader(get, src=0, device="cpu", index=idx)
+    got2 = {n: load2(n) for n in names}
+    ok = ok and all(torch.equal(got2[n], got[n]) for n in names) and load2.stats["tensors"] == len(names)
     q.put((rank, ok, len(got)))
     dist.destroy_process_group()
 

@@ -152,30 +152,40 @@ class ShardedVSM:
         return fetch
 
 
-def broadcast_loader(get, src=0, group=None, device="cuda", bucket_bytes=256 << 20):
+def broadcast_loader(get, src=0, group=None, device="cuda", index=None):
     """Weight broadcast at start-up: only rank `src` reads the checkpoint; every rank builds its replica
     through the returned `name -> tensor` callable, which on `src` loads the tensor and broadcasts it (NCCL over NVLink on
     the GPUs, gloo on CPU) and elsewhere receives it.  All ranks must request the same names in the same order - which they
     do, because `CoreWeights` / `VSMWeights` / `VQAWeights` walk the reference's key layout deterministically.
-    `get` may be None on the other ranks.  `load.stats` counts tensors / bytes / seconds spent in the broadcasts."""
-    import time
+    `get` may be None on the other ranks.
+
+    index: {name: (shape, dtype)} known on `src` (a `SafetensorsStream` carries one in `.index`; bench.py passes its synthetic
+    shape table).  It is broadcast ONCE here, so the per-tensor path is a single `dist.broadcast` with no object exchange;
+    without an index every tensor's shape/dtype is sent first (one small object broadcast per tensor).
+    `load.stats` counts tensors / bytes."""
     rank = dist.get_rank(group)
     stats = dict(tensors=0, bytes=0, seconds=0.0)
+    if rank == src and index is None and hasattr(get, "index"):
+        index = {k: (tuple(v[2]), v[1]) for k, v in get.index.items()}          # SafetensorsStream: (file, dtype, shape, begin, end)
+    box = [index if rank == src else None]
+    dist.broadcast_object_list(box, src=src, group=group)
+    index = box[0]
 
     def load(name):
         if rank == src:
             t = get(name).to(device)
-            meta = [(tuple(t.shape), t.dtype)]
+        if index is not None and name in index:
+            shape, dtype = index[name]
+            if rank == src:
+                assert tuple(t.shape) == tuple(shape) and t.dtype == dtype, (name, t.shape, shape, t.dtype, dtype)
         else:
-            t, meta = None, [None]
-        dist.broadcast_object_list(meta, src=src, group=group)
-        shape, dtype = meta[0]
+            meta = [(tuple(t.shape), t.dtype)] if rank == src else [None]
+            dist.broadcast_object_list(meta, src=src, group=group)
+            shape, dtype = meta[0]
         if rank != src:
             t = torch.empty(shape, dtype=dtype, device=device)
         t = t.contiguous()
-        t0 = time.perf_counter()
         dist.broadcast(t, src=src, group=group)
-        stats["seconds"] += time.perf_counter() - t0
         stats["tensors"] += 1
         stats["bytes"] += t.numel() * t.element_size()
         return t
