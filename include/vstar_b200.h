@@ -44,6 +44,17 @@ int vsb_set_batch_invariant(int on);
 int vsb_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
                   const void* bias, const void* residual, long long ldr, int epilogue, int out_fp32, int rows_per_group,
                   long long group_stride, long long group_offset, void* stream);
+/* vsb_gemm_bf16 with HF LlamaRMSNorm (modeling_llama.py:53-67) FOLDED IN; the norm weight must already be multiplied into W's columns.
+ * rowsq_in != NULL: output row m is scaled by rsqrt(sum_c rowsq_in[c*sq_ld + m] / K + eps) before bias / activation, i.e. A is the
+ * UN-normalised residual stream and 1/rms is applied in the epilogue (no norm kernel, no normalised copy of the activations).
+ * rowsq_out != NULL (bf16 output, N % 32 == 0): also writes the sum of squares of every stored 32-value chunk,
+ * rowsq_out[(n/32)*sq_ld + row], which the next folded GEMM consumes with sq_in_chunks = N/32.  tcgen05 kernels for any M. */
+int vsb_gemm_rowscale_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
+                           const void* bias, const void* residual, long long ldr, int epilogue, int rows_per_group, long long group_stride,
+                           long long group_offset, const void* rowsq_in, int sq_in_chunks, float eps, void* rowsq_out, long long sq_ld,
+                           void* stream);
+/* per-row sum of squares (fp32) of a bf16 matrix: the first rowsq_in of a chain of folded GEMMs (sq_in_chunks = 1) */
+int vsb_rowsq_bf16(const void* x, long long ldx, void* out_f32, int rows, int cols, void* stream);
 /* CUDA-event profiling of every vsb_gemm_bf16 launch (bench.py's roofline leg): begin clears the record; end synchronises
  * and returns the summed algorithmic flops (2*M*N*K), the summed event durations in ms and the launch count. */
 int vsb_gemm_profile_begin(void);
@@ -97,7 +108,10 @@ int vsb_copy2d_b16(const void* src, long long lds, void* dst, long long ldd, lon
  * the last tail_rows rows of every sequence, so the LAST layer runs attention / o-proj / MLP on those rows only (all other
  * rows of x are left at their layer n-1 value); 0 = every row.  q_seg int32 [B*Tn] (with positions): the new rows are several
  * CONTINUATIONS of the cached prefix appended back to back (answer options, vstar_bench_eval.py:127-163): row r attends the
- * prefix keys [0, seg_lo) and its own continuation from key q_seg[r] on (vsb_flash_attn_seg_bf16).  8 kernel launches per layer. */
+ * prefix keys [0, seg_lo) and its own continuation from key q_seg[r] on (vsb_flash_attn_seg_bf16).  norm_folded != 0: the caller
+ * has multiplied ln1 into wqkv's columns and ln2 into wgu's (ln1 / ln2 then hold ones): the QKV and gate|up GEMMs take the
+ * un-normalised residual stream and apply 1/rms in their epilogue, fed by the row statistics the o-proj / down-proj GEMMs leave
+ * (vsb_gemm_rowscale_bf16) - 6 kernel launches per layer instead of 8. */
 typedef struct {
   const void* ln1;
   const void* wqkv;
@@ -108,7 +122,7 @@ typedef struct {
 } vsb_llama_layer_t;
 int vsb_llama_layers(const vsb_llama_layer_t* layers, int n_layers, void* x, int B, int Tn, int past, void* cache, int Bc, int Tmax,
                      int d, int H, int inter, float rms_eps, const void* rope_cos, const void* rope_sin, const void* positions,
-                     const void* k_start, int tail_rows, const void* q_seg, int seg_lo, void* scratch, void* stream);
+                     const void* k_start, int tail_rows, const void* q_seg, int seg_lo, int norm_folded, void* scratch, void* stream);
 
 /* softmax(QK^T*scale [+causal]) V, head_dim 64/128; element (b,s,h,d) at base + b*bs + s*rs + h*D + d.
  * HF CLIP/OWL attention (modeling_clip.py:261-329) and Llama attention (modeling_llama.py:199-221). */

@@ -50,9 +50,14 @@ def test_sharded_checkpoint_roundtrip(tmp_path):
         bf = lambda t: t.to(torch.bfloat16)
         L0 = w.layers[0]
         p = "model.layers.0."
-        assert torch.equal(L0["wqkv"], torch.cat([bf(sd[p + "self_attn.q_proj.weight"]), bf(sd[p + "self_attn.k_proj.weight"]),
-                                                  bf(sd[p + "self_attn.v_proj.weight"])], 0))
-        assert torch.equal(L0["wgu"][0::2], bf(sd[p + "mlp.gate_proj.weight"])) and torch.equal(L0["wgu"][1::2], bf(sd[p + "mlp.up_proj.weight"]))
+        # the RMSNorm weights are folded into the projections that consume the normalised activations (engine.CoreWeights)
+        fold = lambda w_, ln: (bf(w_).float() * bf(sd[p + ln]).float()[None, :]).to(torch.bfloat16)
+        assert w.fold_norms and torch.equal(L0["ln1"], torch.ones_like(L0["ln1"]))
+        assert torch.equal(L0["wqkv"], torch.cat([fold(sd[p + "self_attn.q_proj.weight"], "input_layernorm.weight"),
+                                                  fold(sd[p + "self_attn.k_proj.weight"], "input_layernorm.weight"),
+                                                  fold(sd[p + "self_attn.v_proj.weight"], "input_layernorm.weight")], 0))
+        assert torch.equal(L0["wgu"][0::2], fold(sd[p + "mlp.gate_proj.weight"], "post_attention_layernorm.weight"))
+        assert torch.equal(L0["wgu"][1::2], fold(sd[p + "mlp.up_proj.weight"], "post_attention_layernorm.weight"))
         assert torch.equal(w.clip["patch_w"][:, :588], bf(sd[clip_pfx + "vision_model.embeddings.patch_embedding.weight"]).reshape(-1, 588))
         assert w.cls_w.shape == (cfg.owl_query_dim + 2, cfg.owl_hidden)
         conv = bf(sd["model.mask_decoder.output_upscaling.0.conv.weight"])

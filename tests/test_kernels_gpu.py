@@ -521,6 +521,44 @@ def test_owl_head_epilogues_bf16_values(ops):
     assert torch.equal(b1, b1.to(BF).float()) and float((b1 != want).float().mean()) < 1e-3 and float((b1 - b0).abs().max()) < 1.2e-2
 
 
+def test_gemm_with_folded_rmsnorm(ops):
+    """vsb_gemm_rowscale_bf16: (a) rstd applied in the epilogue == LlamaRMSNorm then GEMM up to bf16 rounding (the fused form skips
+    two roundings of the activations), (b) the row statistics a producer leaves are the sums of squares of exactly the bf16 values
+    it stored, (c) a chain producer -> consumer equals rmsnorm(x_new) @ W, (d) bit-identical rows for any M"""
+    torch.manual_seed(1)
+    M, d, inter = 700, 4096, 11008
+    x = (torch.randn(M, d, device="cuda") * 1.5).to(BF)
+    gamma = (1 + 0.1 * torch.randn(d, device="cuda")).to(BF)
+    w = (torch.randn(1024, d, device="cuda") / math.sqrt(d)).to(BF)
+    wf = (w.float() * gamma.float()[None, :]).to(BF)
+    ref = ops.gemm(ops.rmsnorm(x, gamma, 1e-6), w)
+    out = torch.empty(M, 1024, dtype=BF, device="cuda")
+    ops.gemm_rowscale(x, wf, out, rowsq_in=ops.rowsq(x), eps=1e-6)
+    assert rel_err(out, ref) < 1.5e-2
+    want = ((x.float() * torch.rsqrt((x.float() ** 2).mean(-1, keepdim=True) + 1e-6)) @ wf.float().T)
+    assert rel_err(out, want) < 6e-3                      # closer to exact arithmetic than the two-rounding reference form
+    # producer: o-proj-like GEMM with residual, leaves row statistics of what it stored
+    a = (torch.randn(M, d, device="cuda") * 0.5).to(BF)
+    wo = (torch.randn(d, d, device="cuda") / math.sqrt(d)).to(BF)
+    xn = x.clone()
+    sq = torch.empty(d // 32, M, dtype=torch.float32, device="cuda")
+    ops.gemm_rowscale(a, wo, xn, rowsq_out=sq, residual=xn)
+    assert torch.equal(xn, ops.gemm(a, wo, residual=x.clone()))                       # same values as the plain GEMM
+    want_sq = (xn.float() ** 2).view(M, d // 32, 32).sum(-1).T
+    assert torch.allclose(sq, want_sq, rtol=1e-5, atol=1e-4)
+    # consumer of those statistics (SwiGLU epilogue, interleaved gate/up rows)
+    wgu = (torch.randn(2 * 512, d, device="cuda") / math.sqrt(d)).to(BF)
+    wguf = (wgu.float() * gamma.float()[None, :]).to(BF)
+    g1 = torch.empty(M, 512, dtype=BF, device="cuda")
+    ops.gemm_rowscale(xn, wguf, g1, rowsq_in=sq, eps=1e-6, epilogue=ops.EPI_SWIGLU)
+    g0 = ops.gemm(ops.rmsnorm(xn, gamma, 1e-6), wgu, epilogue=ops.EPI_SWIGLU)
+    assert rel_err(g1, g0) < 2e-2
+    for m in (5, 40, 300):                                                           # row results do not depend on M
+        o2 = torch.empty(m, 512, dtype=BF, device="cuda")
+        ops.gemm_rowscale(xn[:m].contiguous(), wguf, o2, rowsq_in=sq[:, :m].contiguous(), eps=1e-6, epilogue=ops.EPI_SWIGLU)
+        assert torch.equal(o2, g1[:m])
+
+
 def test_rows_invariant_to_batch(ops):
     """batch-invariant mode (vsb_set_batch_invariant): the first rows of a GEMM / RMSNorm are bit-identical whether the call
     carries 3, 16, 320, 2264 or 18112 rows - i.e. the tcgen05 tile variants (32/64/128/256 wide, 2-CTA) accumulate every
@@ -625,3 +663,23 @@ def test_llama_layers_native_runner(ops):
         assert not torch.equal(xf.view(B, 70, d)[:, :-tail], xt.view(B, 70, d)[:, :-tail])   # the other rows were indeed skipped
     with pytest.raises(Exception):
         native_stack(rnd(B * 30, d, seed=112), torch.zeros(nl, B, Tmax, 3 * d, dtype=BF, device="cuda"), 30, 70)    # exceeds Tmax
+    # folded RMSNorm: ln1 / ln2 multiplied into wqkv / wgu, 1/rms applied in the GEMM epilogues (6 launches per layer).  Against the
+    # unfused runner on the SAME folded weights (ln = 1): equal up to bf16 rounding; tail rows bit-identical to the full fused pass.
+    ones = torch.ones(d, dtype=BF, device="cuda")
+    folded = [dict(ln1=ones, ln2=ones, wqkv=(L["wqkv"].float() * L["ln1"].float()[None, :]).to(BF).contiguous(), wo=L["wo"],
+                   wgu=(L["wgu"].float() * L["ln2"].float()[None, :]).to(BF).contiguous(), wdown=L["wdown"]) for L in layers]
+    ftable = ops.llama_layer_table(folded)
+    res = {}
+    for fused in (False, True):
+        cache = torch.zeros(nl, B, Tmax, 3 * d, dtype=BF, device="cuda")
+        xx = rnd(B * 70, d, seed=110).clone()
+        ops.llama_layers(ftable, nl, xx, B, 70, 0, cache, B, Tmax, d, H, inter, 1e-6, cos_t, sin_t, scratch, norm_folded=fused)
+        res[fused] = (xx.clone(), cache.clone())
+    torch.cuda.synchronize()
+    assert rel_err(res[True][0], res[False][0]) < 3e-2 and rel_err(res[True][1], res[False][1]) < 3e-2
+    assert rel_err(res[True][0], outs[1][0]) < 3e-2                                  # and to the un-folded weights with their norms
+    cache_t = torch.zeros_like(cache_f)
+    xt = rnd(B * 70, d, seed=110).clone()
+    ops.llama_layers(ftable, nl, xt, B, 70, 0, cache_t, B, Tmax, d, H, inter, 1e-6, cos_t, sin_t, scratch, tail_rows=9, norm_folded=True)
+    torch.cuda.synchronize()
+    assert torch.equal(cache_t, res[True][1]) and torch.equal(xt.view(B, 70, d)[:, -9:], res[True][0].view(B, 70, d)[:, -9:])

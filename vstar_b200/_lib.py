@@ -36,7 +36,9 @@ SIGNATURES = {
     "vsb_nll_rows_f32": [c_p, c_ll, c_i, c_i, c_p, c_p, c_p],
     "vsb_argmax_rows_f32": [c_p, c_ll, c_i, c_i, c_p, c_p, c_p],
     "vsb_copy2d_b16": [c_p, c_ll, c_p, c_ll, c_ll, c_i, c_p],
-    "vsb_llama_layers": [c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_i, c_p, c_i, c_p, c_p],
+    "vsb_llama_layers": [c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_i, c_p, c_i, c_i, c_p, c_p],
+    "vsb_gemm_rowscale_bf16": [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_p, c_p, c_ll, c_i, c_i, c_ll, c_ll, c_p, c_i, c_f, c_p, c_ll, c_p],
+    "vsb_rowsq_bf16": [c_p, c_ll, c_p, c_i, c_i, c_p],
     "vsb_flash_attn_seg_bf16": [c_p, c_p, c_p, c_p, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_i, c_p],
     "vsb_attn_decode_bf16": [c_p, c_p, c_p, c_p, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p],
     "vsb_flash_attn_bf16": [c_p, c_p, c_p, c_p, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],

@@ -419,6 +419,34 @@ extern "C" int vsb_rmsnorm_bf16(const void* x, long long ldx, const void* w, voi
   return VSB_OK;
 }
 
+// sum of squares of every row (fp32), the input side of a folded RMSNorm (vsb_gemm_rowscale_bf16 with sq_in_chunks = 1);
+// one warp per row, fixed summation order
+__global__ void __launch_bounds__(128) rowsq_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ out, int rows, int cols) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const bf16* xr = x + (long long)row * ldx;
+  float s = 0.f;
+  for (int c = lane * 8; c < cols; c += 256) {
+    const uint4 v = *reinterpret_cast<const uint4*>(xr + c);
+    float2 t;
+    t = unpack_bf16x2(v.x); s = fmaf(t.x, t.x, s); s = fmaf(t.y, t.y, s);
+    t = unpack_bf16x2(v.y); s = fmaf(t.x, t.x, s); s = fmaf(t.y, t.y, s);
+    t = unpack_bf16x2(v.z); s = fmaf(t.x, t.x, s); s = fmaf(t.y, t.y, s);
+    t = unpack_bf16x2(v.w); s = fmaf(t.x, t.x, s); s = fmaf(t.y, t.y, s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) out[row] = s;
+}
+
+extern "C" int vsb_rowsq_bf16(const void* x, long long ldx, void* out_f32, int rows, int cols, void* stream) {
+  VSB_CHECK_ARG(x && out_f32 && cols % 8 == 0 && ldx % 8 == 0, "vsb_rowsq_bf16: bad args (cols, ldx multiples of 8)");
+  if (rows <= 0) return VSB_OK;
+  rowsq_kernel<<<(rows + 3) / 4, 128, 0, STREAM(stream)>>>((const bf16*)x, ldx, (float*)out_f32, rows, cols);
+  VSB_LAUNCH_CHECK();
+  return VSB_OK;
+}
+
 extern "C" int vsb_rope_bf16(void* qkv, long long ld, int rows, int T, int H, int D, int pos0, const void* cos_table,
                              const void* sin_table, const void* positions, long long group_stride, long long group_offset,
                              void* stream) {

@@ -45,6 +45,15 @@ struct GemmParams {
   // reads for 0.33 GB of operands on the gate|up GEMM of a 64-crop batch (profiles/r02_gemm_dram_bytes_before_hints.csv).
   unsigned long long hint_a, hint_b;
   int stream_out;      // output stores with .cs (evict-first) semantics
+  // RMSNorm folded into the GEMM (LlamaRMSNorm with its weight pre-multiplied into W, see vsb_gemm_rowscale_bf16):
+  //   rowsq_in  [sq_in_chunks][sq_ld] fp32: partial sums of squares of the A rows -> output row m is scaled by
+  //             rsqrt(sum_c rowsq_in[c][m] * sq_inv_cols + sq_eps) before bias / activation
+  //   rowsq_out [N/32][sq_ld] fp32: sum of squares of the 32 bf16 OUTPUT values (after residual) of chunk n0/32 of row m
+  const float* rowsq_in;
+  float* rowsq_out;
+  long long sq_ld;
+  int sq_in_chunks;
+  float sq_inv_cols, sq_eps;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -191,10 +200,10 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
 
 // ---------------------------------------------------------------- shared epilogue: 32 fp32 accumulator columns of one row
 // bias -> activation / SwiGLU -> (+residual) -> bf16 / fp32 store (16 B vector stores when aligned)
-__device__ __forceinline__ void epilogue_store(const GemmParams& p, const uint32_t* v, long long orow, int n0, bool swiglu) {
+__device__ __forceinline__ void epilogue_store(const GemmParams& p, const uint32_t* v, long long orow, int n0, bool swiglu, float rs = 1.f) {
     float f[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * rs;
     if (p.bias != nullptr) {
       if (n0 + 32 <= p.N) {
         const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
@@ -334,17 +343,17 @@ __device__ __forceinline__ void prefetch_residual(const GemmParams& p, int m_bas
 }
 
 __device__ __forceinline__ void epilogue_store_staged(const GemmParams& p, const uint32_t* v, uint8_t* stage, int m_base, int lane, int n0,
-                                                      bool swiglu, const uint4* rpre) {
+                                                      bool swiglu, const uint4* rpre, float rs = 1.f) {
   const int on0 = swiglu ? (n0 >> 1) : n0;
   const bool fast = epilogue_fast_path(p, n0, swiglu);
   if (!fast) {                                              // warp-uniform
     const int m = m_base + lane;
-    if (m < p.M && n0 < p.N) epilogue_store(p, v, remap_row(p, m), n0, swiglu);
+    if (m < p.M && n0 < p.N) epilogue_store(p, v, remap_row(p, m), n0, swiglu, rs);
     return;
   }
   float f[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * rs;
   if (p.bias != nullptr) {
     const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
 #pragma unroll
@@ -404,6 +413,14 @@ __device__ __forceinline__ void epilogue_store_staged(const GemmParams& p, const
     }
     __syncwarp();
   }
+  if (p.rowsq_out != nullptr) {
+    // sum of squares of this row's 32 output values AS STORED (bf16): the next GEMM reads exactly these and normalises with them
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { const float r = rbf(f[j]); sq = fmaf(r, r, sq); }
+    const int m = m_base + lane;
+    if (m < p.M) p.rowsq_out[(long long)(n0 >> 5) * p.sq_ld + remap_row(p, m)] = sq;
+  }
 #pragma unroll
   for (int j4 = 0; j4 < 4; ++j4) {
     uint4 w;
@@ -424,6 +441,14 @@ __device__ __forceinline__ void epilogue_store_staged(const GemmParams& p, const
     }
   }
   __syncwarp();
+}
+
+// 1 / rms of A row m from the partial sums a producer GEMM (or vsb_rowsq_bf16) left behind; fixed summation order
+__device__ __forceinline__ float row_rstd(const GemmParams& p, int m) {
+  if (p.rowsq_in == nullptr || m >= p.M) return 1.f;
+  float s = 0.f;
+  for (int c = 0; c < p.sq_in_chunks; ++c) s += p.rowsq_in[(long long)c * p.sq_ld + m];
+  return rsqrtf(s * p.sq_inv_cols + p.sq_eps);
 }
 
 constexpr int GEMM_THREADS = 384;   // warps 0-3: TMA / MMA / TMEM-alloc / spare; warps 4-11: epilogue (2 per TMEM lane quarter)
@@ -533,9 +558,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, m_blk, n_blk);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      const int m = m_blk * BM + q * 32 + lane;
+      const float rs = row_rstd(p, m);        // (folded RMSNorm) fetched while the tile's MMAs are still running
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int m = m_blk * BM + q * 32 + lane;
       const bool row_ok = m < p.M;
       long long orow = 0;
       if (row_ok) orow = (long long)(m / p.rows_per_group) * p.group_stride + p.group_offset + (m % p.rows_per_group);
@@ -553,7 +579,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         tmem_ld_wait();
         const int n0 = n_blk * BN + c * 32;
         if (n0 >= p.N) continue;                      // warp-uniform
-        epilogue_store_staged(p, v, smem + L::EPI_OFFSET + (warp - 4) * EPI_WARP_BYTES, m_base, lane, n0, swiglu, rcur);
+        epilogue_store_staged(p, v, smem + L::EPI_OFFSET + (warp - 4) * EPI_WARP_BYTES, m_base, lane, n0, swiglu, rcur, rs);
       }
       // release this accumulator buffer to the MMA warp
       tc_fence_before();
@@ -757,9 +783,10 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, m_blk, n_blk);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      const int m = m_blk * 256 + (int)rank * 128 + q * 32 + lane;
+      const float rs = row_rstd(p, m);        // (folded RMSNorm) fetched while the tile's MMAs are still running
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int m = m_blk * 256 + (int)rank * 128 + q * 32 + lane;
       const bool row_ok = m < p.M;
       long long orow = 0;
       if (row_ok) orow = (long long)(m / p.rows_per_group) * p.group_stride + p.group_offset + (m % p.rows_per_group);
@@ -777,7 +804,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         tmem_ld_wait();
         const int n0 = n_blk * BN2 + c * 32;
         if (n0 >= p.N) continue;                      // warp-uniform
-        epilogue_store_staged(p, v, smem + L::EPI_OFFSET + (warp - 4) * EPI_WARP_BYTES, m_base, lane, n0, swiglu, rcur);
+        epilogue_store_staged(p, v, smem + L::EPI_OFFSET + (warp - 4) * EPI_WARP_BYTES, m_base, lane, n0, swiglu, rcur, rs);
       }
       tc_fence_before();
       __syncwarp();
@@ -962,17 +989,63 @@ extern "C" int vsb_gemm_profile_end(double* flops, double* ms, long long* launch
   return VSB_OK;
 }
 
+struct RowSq {          // folded-RMSNorm side channels of a GEMM (see vsb_gemm_rowscale_bf16)
+  const float* in;
+  float* out;
+  long long ld;
+  int in_chunks;
+  float inv_cols, eps;
+};
+
 static int gemm_dispatch(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
                          const void* bias, const void* residual, long long ldr, int epilogue, int out_fp32, int rows_per_group,
-                         long long group_stride, long long group_offset, void* stream_);
+                         long long group_stride, long long group_offset, const RowSq* rsq, void* stream_);
+
+static int gemm_profiled(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
+                         const void* bias, const void* residual, long long ldr, int epilogue, int out_fp32, int rows_per_group,
+                         long long group_stride, long long group_offset, const RowSq* rsq, void* stream_);
 
 extern "C" int vsb_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M,
                              int N, int K, const void* bias, const void* residual, long long ldr, int epilogue,
                              int out_fp32, int rows_per_group, long long group_stride, long long group_offset,
                              void* stream_) {
+  return gemm_profiled(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, epilogue, out_fp32, rows_per_group, group_stride, group_offset,
+                       nullptr, stream_);
+}
+
+// GEMM with LlamaRMSNorm folded in (the norm weight must already be multiplied into W's columns):
+//   rowsq_in  != NULL: C row m = epi(rsqrt(sum_c rowsq_in[c*sq_ld + m] / K + eps) * (A[m] . W^T) + bias) (+ residual), i.e. the GEMM
+//                      reads the UN-normalised residual stream and applies 1/rms in its epilogue (fp32) - no norm kernel, no
+//                      normalised copy of the activations
+//   rowsq_out != NULL: additionally writes, for every output row and 32-column chunk, the sum of squares of the bf16 values it
+//                      stored: rowsq_out[(n/32)*sq_ld + row]; the next folded GEMM consumes them with sq_in_chunks = N/32.
+// bf16 output, N % 32 == 0 when rowsq_out is given.  Always the tcgen05 kernels (any M).
+extern "C" int vsb_gemm_rowscale_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N,
+                                      int K, const void* bias, const void* residual, long long ldr, int epilogue, int rows_per_group,
+                                      long long group_stride, long long group_offset, const void* rowsq_in, int sq_in_chunks, float eps,
+                                      void* rowsq_out, long long sq_ld, void* stream_) {
+  VSB_CHECK_ARG(rowsq_in || rowsq_out, "vsb_gemm_rowscale_bf16: neither rowsq_in nor rowsq_out given (use vsb_gemm_bf16)");
+  VSB_CHECK_ARG(sq_ld >= M && (!rowsq_in || sq_in_chunks > 0), "vsb_gemm_rowscale_bf16: bad sq_ld / sq_in_chunks");
+  VSB_CHECK_ARG(!rowsq_out || (N % 32 == 0 && ldc % 8 == 0 && epilogue != VSB_EPI_SWIGLU && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+                               (residual == nullptr || (ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0))),
+                "vsb_gemm_rowscale_bf16: rowsq_out needs N %% 32 == 0 and 16-byte aligned bf16 rows");
+  RowSq r;
+  r.in = reinterpret_cast<const float*>(rowsq_in);
+  r.out = reinterpret_cast<float*>(rowsq_out);
+  r.ld = sq_ld;
+  r.in_chunks = sq_in_chunks;
+  r.inv_cols = 1.f / (float)K;
+  r.eps = eps;
+  return gemm_profiled(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, epilogue, 0, rows_per_group, group_stride, group_offset, &r,
+                       stream_);
+}
+
+static int gemm_profiled(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
+                         const void* bias, const void* residual, long long ldr, int epilogue, int out_fp32, int rows_per_group,
+                         long long group_stride, long long group_offset, const RowSq* rsq, void* stream_) {
   if (!g_prof_on)
     return gemm_dispatch(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, epilogue, out_fp32, rows_per_group, group_stride,
-                         group_offset, stream_);
+                         group_offset, rsq, stream_);
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ProfRec r;
   VSB_CUDA(cudaEventCreate(&r.a));
@@ -980,7 +1053,7 @@ extern "C" int vsb_gemm_bf16(const void* A, long long lda, const void* W, long l
   r.flops = 2.0 * (double)M * (double)N * (double)K;
   VSB_CUDA(cudaEventRecord(r.a, stream));
   const int rc = gemm_dispatch(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, epilogue, out_fp32, rows_per_group, group_stride,
-                               group_offset, stream_);
+                               group_offset, rsq, stream_);
   VSB_CUDA(cudaEventRecord(r.b, stream));
   g_prof.push_back(r);
   return rc;
@@ -989,7 +1062,7 @@ extern "C" int vsb_gemm_bf16(const void* A, long long lda, const void* W, long l
 static int gemm_dispatch(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M,
                              int N, int K, const void* bias, const void* residual, long long ldr, int epilogue,
                              int out_fp32, int rows_per_group, long long group_stride, long long group_offset,
-                             void* stream_) {
+                             const RowSq* rsq, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VSB_CHECK_ARG(A && W && C, "vsb_gemm_bf16: null pointer");
   VSB_CHECK_ARG(M > 0 && N > 0 && K > 0, "vsb_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
@@ -1016,11 +1089,17 @@ static int gemm_dispatch(const void* A, long long lda, const void* W, long long 
   p.rows_per_group = rows_per_group;
   p.group_stride = group_stride;
   p.group_offset = group_offset;
+  p.rowsq_in = rsq ? rsq->in : nullptr;
+  p.rowsq_out = rsq ? rsq->out : nullptr;
+  p.sq_ld = rsq ? rsq->ld : 0;
+  p.sq_in_chunks = rsq ? rsq->in_chunks : 0;
+  p.sq_inv_cols = rsq ? rsq->inv_cols : 0.f;
+  p.sq_eps = rsq ? rsq->eps : 0.f;
 
   // decode-sized problems are HBM-bound on W: CUDA-core streaming kernel (gemm_skinny.cu); force_bn = 1 forces it (tests)
   // measured (tools/bench_vqa.py, CUDA-graph timing, fraction of the HBM roofline): FMA kernel 0.57-0.96 at M = 1; mma.sync
   // kernel 0.44-0.79 for M = 2..8 (and ahead of the tcgen05 tiles on N <= 8192 up to M = 16); tcgen05 tiles 0.26-0.76 at M = 16
-  if ((K % 8) == 0 && !(vsb_batch_invariant() && g_force_bn == 0)) {
+  if ((K % 8) == 0 && !(vsb_batch_invariant() && g_force_bn == 0) && rsq == nullptr) {
     int variant = 0;
     if (g_force_bn == 1 && M <= 8) variant = 1;
     else if (g_force_bn == 2 && M <= 16) variant = 2;

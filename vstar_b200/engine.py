@@ -53,15 +53,26 @@ class CoreWeights:
         self.lm_head = g("lm_head.weight")
         self.final_norm = g("model.norm.weight")
         self.layers = []
+        self.fold_norms = os.environ.get("VSB_FOLD_NORMS", "1") != "0"
+        ones = None
         for i in range(c.n_layers):
             p = f"model.layers.{i}."
             wqkv = torch.cat([g(p + "self_attn.q_proj.weight"), g(p + "self_attn.k_proj.weight"), g(p + "self_attn.v_proj.weight")], 0)
             gate, up = g(p + "mlp.gate_proj.weight"), g(p + "mlp.up_proj.weight")
             wgu = torch.stack([gate, up], dim=1).reshape(2 * c.intermediate, c.hidden).contiguous()   # row 2j = gate_j, 2j+1 = up_j
             del gate, up
-            self.layers.append(dict(wqkv=wqkv.contiguous(), wo=g(p + "self_attn.o_proj.weight"), wgu=wgu,
-                                    wdown=g(p + "mlp.down_proj.weight"), ln1=g(p + "input_layernorm.weight"),
-                                    ln2=g(p + "post_attention_layernorm.weight")))
+            ln1, ln2 = g(p + "input_layernorm.weight"), g(p + "post_attention_layernorm.weight")
+            if self.fold_norms:
+                # LlamaRMSNorm's weight folded into the consuming projections: w * (x * rstd) @ W^T == rstd * (x @ (W * w)^T).  The
+                # kernels then apply 1/rms in the GEMM epilogue (vsb_gemm_rowscale_bf16) and no norm kernel runs; ln1 / ln2 become
+                # ones so that the unfused decode path (skinny GEMMs) computes the same function from the same folded weights.
+                wqkv = (wqkv.float() * ln1.float()[None, :]).to(BF)
+                wgu = (wgu.float() * ln2.float()[None, :]).to(BF)
+                if ones is None:
+                    ones = torch.ones_like(ln1)
+                ln1 = ln2 = ones
+            self.layers.append(dict(wqkv=wqkv.contiguous(), wo=g(p + "self_attn.o_proj.weight"), wgu=wgu.contiguous(),
+                                    wdown=g(p + "mlp.down_proj.weight"), ln1=ln1, ln2=ln2))
         # RoPE tables exactly as HF builds them (fp32 outer product -> cos/sin -> bf16)
         hd = c.head_dim
         inv = 1.0 / (c.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd))
@@ -312,7 +323,8 @@ class LlamaClipCore:
         scratch = torch.empty((B * Tn * (2 * c.hidden + c.intermediate),), dtype=BF, device=self.dev)
         return ops.llama_layers(self._layer_table, len(self.w.layers), x, B, Tn, past, self._cache, Bc, Tm, c.hidden, c.n_heads,
                                 c.intermediate, c.rms_eps, self.w.rope_cos, self.w.rope_sin, scratch, positions=positions,
-                                k_start=k_start, cache_row_offset=cache_row_offset, tail_rows=tail_rows, q_seg=q_seg, seg_lo=seg_lo)
+                                k_start=k_start, cache_row_offset=cache_row_offset, tail_rows=tail_rows, q_seg=q_seg, seg_lo=seg_lo,
+                                norm_folded=getattr(self.w, "fold_norms", False))
 
     def _logits_rows(self, x, rows):
         """final RMSNorm + lm_head on selected rows of the residual stream -> (hidden [n,d], argmax [n], logits fp32 [n,V])"""

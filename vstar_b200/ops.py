@@ -84,13 +84,14 @@ def llama_layer_table(layers):
 
 
 def llama_layers(table, n_layers, x, B, Tn, past, cache, Bc, Tmax, d, H, inter, eps, rope_cos, rope_sin, scratch, positions=None,
-                 k_start=None, cache_row_offset=0, tail_rows=0, q_seg=None, seg_lo=0):
+                 k_start=None, cache_row_offset=0, tail_rows=0, q_seg=None, seg_lo=0, norm_folded=False):
     """whole decoder stack in ONE native call (csrc/llama_layers.cu): in place on x [B*Tn, d].
     cache_row_offset shifts the cache origin by that many [3d] rows (a sequence placed at batch slot b, first row s:
     b*Tmax + s) so a single sequence can be prefilled anywhere in a shared cache; positions / k_start: ragged decode;
     tail_rows > 0: only the last tail_rows rows of every sequence are valid on return (the last layer skips the others);
     q_seg int32 [B*Tn] + seg_lo: the new rows are several continuations of the cached prefix [0, seg_lo) appended back to back;
-    row r attends the prefix and its own continuation from key q_seg[r] on."""
+    row r attends the prefix and its own continuation from key q_seg[r] on;
+    norm_folded: ln1 / ln2 are already multiplied into wqkv / wgu (fused RMSNorm path, see vsb_llama_layers)."""
     _chk(x, BF16), _chk(cache, BF16), _chk(scratch, BF16)
     assert x.is_contiguous() and cache.is_contiguous() and x.shape == (B * Tn, d)
     assert scratch.numel() >= B * Tn * (2 * d + inter)
@@ -99,10 +100,11 @@ def llama_layers(table, n_layers, x, B, Tn, past, cache, Bc, Tmax, d, H, inter, 
     assert q_seg is None or (q_seg.numel() == B * Tn and positions is not None)
     assert positions is None or positions.numel() == B * Tn
     assert k_start is None or k_start.numel() == B
-    _lib.launches += 8 * n_layers + (2 if (tail_rows > 0 and 2 * tail_rows <= Tn and k_start is None) else 0)
+    _lib.launches += (6 if (norm_folded and k_start is None and (B * Tn > 16 or batch_invariant.depth > 0)) else 8) * n_layers + \
+        (2 if (tail_rows > 0 and 2 * tail_rows <= Tn and k_start is None) else 0)
     call("vsb_llama_layers", table, n_layers, x.data_ptr(), B, Tn, past, cache.data_ptr() + cache_row_offset * 3 * d * 2, Bc, Tmax, d, H,
          inter, float(eps), rope_cos.data_ptr(), rope_sin.data_ptr(), _p(positions), _p(k_start), int(tail_rows), _p(q_seg), int(seg_lo),
-         scratch.data_ptr(), _stream())
+         1 if norm_folded else 0, scratch.data_ptr(), _stream())
     return x
 
 
@@ -128,6 +130,32 @@ def gemm(a, w, out=None, bias=None, residual=None, epilogue=EPI_NONE, out_dtype=
     call("vsb_gemm_bf16", pa, lda, pw, ldw, out.data_ptr(), out.stride(0), M, N, K, _p(bias), _p(residual),
          residual.stride(0) if residual is not None else 0, epilogue, out_fp32, rows_per_group, group_stride, group_offset,
          _stream())
+    return out
+
+
+def gemm_rowscale(a, w, out, rowsq_in=None, rowsq_out=None, eps=1e-6, residual=None, epilogue=EPI_NONE):
+    """out = epi(rstd[m] * (a @ w.T)) (+ residual) with the RMSNorm weight already folded into w; rowsq_in fp32 [chunks, M] partial
+    sums of squares of a's rows, rowsq_out fp32 [N/32, M] receives those of the stored output (see vsb_gemm_rowscale_bf16)"""
+    _chk(a, BF16), _chk(w, BF16), _chk(out, BF16)
+    pa, M, K, lda = _rows2d(a)
+    pw, N, K2, ldw = _rows2d(w)
+    assert K == K2 and out.stride(1) == 1
+    for t in (rowsq_in, rowsq_out):
+        assert t is None or (t.dtype == torch.float32 and t.is_cuda and t.is_contiguous() and t.shape[1] == M)
+    _lib.launches += 1
+    call("vsb_gemm_rowscale_bf16", pa, lda, pw, ldw, out.data_ptr(), out.stride(0), M, N, K, 0, _p(residual),
+         residual.stride(0) if residual is not None else 0, epilogue, 0, 0, 0, _p(rowsq_in), rowsq_in.shape[0] if rowsq_in is not None else 0,
+         float(eps), _p(rowsq_out), M, _stream())
+    return out
+
+
+def rowsq(x):
+    """fp32 [1, rows] sums of squares of the rows of x (bf16)"""
+    _chk(x, BF16)
+    px, rows, cols, ldx = _rows2d(x)
+    out = torch.empty((1, rows), dtype=torch.float32, device=x.device)
+    _lib.launches += 1
+    call("vsb_rowsq_bf16", px, ldx, out.data_ptr(), rows, cols, _stream())
     return out
 
 
