@@ -323,7 +323,7 @@ class SearchState:
 class SearchController:
     """Runs one or many SearchStates against a vsm object, batching (and pipelining) node evaluations."""
 
-    def __init__(self, vsm, scorer=None, batch_size=1, extract_noun_chunks=None, depth=2, split_min=8):
+    def __init__(self, vsm, scorer=None, batch_size=1, extract_noun_chunks=None, depth=2, split_min=8, speculate_children=True):
         self.vsm = vsm
         self.scorer = scorer if scorer is not None else CudaScorer()
         self.batch_size = max(1, int(batch_size))
@@ -338,6 +338,7 @@ class SearchController:
         self.pipelined = hasattr(vsm, "detect_regions_launch")
         self.depth = max(1, int(depth))
         self.split_min = split_min
+        self.speculate_children = speculate_children
         self.batches = []              # sizes of the launched batches (diagnostics)
         self.cue_batches = []          # (kind, size) of the batched weak-cue calls
 
@@ -534,7 +535,9 @@ class SearchController:
 
     def _select(self, active, limit):
         """mandatory nodes first (the current node of every search that is not already in flight), then fill the batch with
-        speculation, round-robin over the active searches"""
+        speculation, round-robin over the active searches: the best queue entries, and - if the batch still has room - the
+        CHILDREN of the nodes being evaluated (their geometry is known before the parent commits, visual_search.py:234-253), so
+        that a search whose frontier is one node deep does not pay one GPU round per tree level"""
         reqs = [(st, st.current) for st in active if st._free(st.current)][:limit]
         room = limit - len(reqs)
         if room > 0 and active:
@@ -546,6 +549,21 @@ class SearchController:
                     if all(p is not t for t in taken):
                         extra.append((st, p))
             reqs += extra[:room]
+            room = limit - len(reqs)
+        if room > 0 and self.speculate_children:
+            seen = {(id(st), st.key(p)) for st, p in reqs}
+            kids = []
+            for st, p in list(reqs):
+                bb = p["bbox"]
+                if not expandable(bb, st.smallest_size):
+                    continue
+                subs, _, _ = get_sub_patches(bb, *split_4subpatches(bb))
+                for sp in subs:
+                    node = dict(bbox=sp, scale_level=p["scale_level"] + 1, score=None, parent_index=None)     # evaluation only
+                    if st._free(node) and (id(st), st.key(node)) not in seen:
+                        seen.add((id(st), st.key(node)))
+                        kids.append((st, node))
+            reqs += kids[:room]
         return reqs
 
     def run(self, states):
