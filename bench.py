@@ -556,7 +556,7 @@ def run_b200(args):
                                          "T=320; %d constant prefix rows per crop are served from the shared-prefix KV snapshot, and the last "
                                          "decoder layer runs o-proj/MLP on the 5 consumed rows only)" % (flops_per_crop / 1e12, prefix_rows))},
         "crops_per_step": dev_crops // args.steps, "load_s": load_s,
-        "draft_verify": dict(engine.stats),
+        "draft_verify": engine.stats,          # (live dict: also counts the graph captures / replays of the later legs)
         "weight_broadcast": bcast,
         "parity_in_run": {"trajectories_identical_across_steps_and_legs": True,
                           "vqa_choices": st2["trajectories"][1]},

@@ -312,9 +312,9 @@ class VSM:
             # Search images that are not resident yet cost ~1.5 ms of host time each (PIL -> pinned staging -> H2D).  Such a
             # group is cut into chunks whose engine work is launched WITHOUT waiting for the GPU (defer=True), so the host
             # converts the next chunk's images while the GPU evaluates the previous one.
-            fresh = sum(1 for i in members if self.prep == "gpu" and id(regions[i][0]) not in self._resident)
+            fresh = len({id(regions[i][0]) for i in members if self.prep == "gpu" and id(regions[i][0]) not in self._resident})
             step = len(members)
-            if self.upload_chunk > 0 and fresh >= 4:
+            if self.upload_chunk > 0 and fresh >= 4:          # (distinct images that still have to be uploaded)
                 # at least two chunks when several images still have to be uploaded: the first engine call starts after half of
                 # the conversions instead of all of them
                 step = max(2, min(self.upload_chunk, (len(members) + 1) // 2))
