@@ -315,6 +315,11 @@ class VSM:
             fresh = len({id(regions[i][0]) for i in members if self.prep == "gpu" and id(regions[i][0]) not in self._resident})
             step = len(members)
             if self.upload_chunk > 0 and fresh >= 4:          # (distinct images that still have to be uploaded)
+                # crops of the same image next to each other: the first chunk then needs only the first few uploads
+                order = {}
+                for i in members:
+                    order.setdefault(id(regions[i][0]), len(order))
+                members = sorted(members, key=lambda i: order[id(regions[i][0])])
                 # at least two chunks when several images still have to be uploaded: the first engine call starts after half of
                 # the conversions instead of all of them
                 step = max(2, min(self.upload_chunk, (len(members) + 1) // 2))
