@@ -619,6 +619,49 @@ def run_b200(args):
         except Exception as e:
             out["weak_cue"] = {"error": repr(e)}
 
+    # ---- full SEAL loop (configs[4] "full SEAL VQA+VSM loop", vstar_bench_eval.py:186-273) on one GPU: free-form answers for 8
+    # images in ONE continuous-batched decode, the guided searches for the "missing objects" (2 per image), option scoring ----
+    if extra and rank == 0 and vqa is not None:
+        try:
+            n_img = 2 if args.tiny else 8
+            l_side, l_small = (256, 64) if args.tiny else (2048, 512)
+            l_images = images_for(n_img, l_side, 8000)
+            new_tokens = 24
+
+            def loop_step():
+                t = {}
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                bg = tuple(int(x * 255) for x in vqa.image_processor.image_mean)
+                padded = [seal.expand2square_center(im, bg)[0] for im in l_images]
+                vqa.free_form_inference_batch(padded, [QUESTION] * n_img, max_new_tokens=new_tokens, originals=l_images)   # random weights: text unused
+                torch.cuda.synchronize(); t["free_form_ms"] = (time.perf_counter() - t0) * 1e3; t1 = time.perf_counter()
+                # random-init weights never emit the "missing objects" sentence: take the canned one the real model gives
+                missing = seal.parse_missing_objects(seal.MISSING_OBJECTS_MSG + " " + ", ".join(TARGETS) + ".")
+                jobs_l = [(im, name, l_small) for im in l_images for name in missing]
+                res_l, _ = visual_search_many(vsm, jobs_l, batch_size=args.batch, depth=args.depth, **kw)
+                torch.cuda.synchronize(); t["search_ms"] = (time.perf_counter() - t1) * 1e3; t2 = time.perf_counter()
+                samples = []
+                for k, im in enumerate(l_images):
+                    sr = seal.collect_search_results(missing, res_l[k * len(missing):(k + 1) * len(missing)])
+                    samples.append((im, QUESTION, OPTIONS, missing, sr))
+                seal.choose_options(vqa, samples)
+                torch.cuda.synchronize(); t["options_ms"] = (time.perf_counter() - t2) * 1e3
+                t["total_ms"] = (time.perf_counter() - t0) * 1e3
+                t["crops"] = len(jobs_l) * 21
+                return t
+
+            loop_step()
+            ts = [loop_step() for _ in range(2)]
+            best = min(ts, key=lambda x: x["total_ms"])
+            vsm.release()
+            out["seal_loop"] = {"workload": f"{n_img} V*Bench-style samples of {l_side}x{l_side} images end to end from PIL images: free-form answer "
+                                            f"(continuous-batched greedy decode, {new_tokens} new tokens forced by max_new_tokens), 2 guided searches per "
+                                            "image (21 crops each, lock-step), option scoring with the found objects (batched)",
+                                "samples_per_s": n_img / (best["total_ms"] / 1e3), "crops_per_s": best["crops"] / (best["total_ms"] / 1e3),
+                                **{k: best[k] for k in ("free_form_ms", "search_ms", "options_ms", "total_ms")}}
+        except Exception as e:
+            out["seal_loop"] = {"error": repr(e)}
+
     # ---- frontier leg: ONE set of searches, every batch sharded over all ranks (strong scaling) ----------------------
     if extra:
         try:

@@ -82,7 +82,7 @@ def eval_model(args, vqa_llm=None, vsm=None, log=print, search_kwargs=None):
             padded = [expand2square_center(smp["image"], bg)[0] for smp in chunk]
             questions = [smp["annotation"]["question"] for smp in chunk]
             if hasattr(vqa_llm, "free_form_inference_batch") and len(chunk) > 1:
-                predictions = vqa_llm.free_form_inference_batch(padded, questions)      # one continuous-batched decode
+                predictions = vqa_llm.free_form_inference_batch(padded, questions, originals=[smp["image"] for smp in chunk])      # one continuous-batched decode
             else:
                 predictions = [vqa_llm.free_form_inference(im, q) for im, q in zip(padded, questions)]
             for smp, prediction in zip(chunk, predictions):

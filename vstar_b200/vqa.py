@@ -563,18 +563,22 @@ class VQA_LLM:
         return text.strip()
 
     @torch.inference_mode()
-    def free_form_inference_batch(self, images, questions, max_new_tokens=200):
+    def free_form_inference_batch(self, images, questions, max_new_tokens=200, originals=None):
         """free_form_inference for several (image, question) pairs in ONE continuous-batched decode (not in the reference,
         which answers one image at a time, vstar_bench_eval.py:196): same prompt, stop string and post-processing per
-        sample; each decode step reads the 7B weights once for the whole batch."""
+        sample; each decode step reads the 7B weights once for the whole batch.  originals: the un-padded images the padded
+        `images` were made from; with `use_device_images` the pixels are then produced on the GPU (bit-identical)."""
         stop_str = "</s>"
         kw = self.tokenizer(stop_str).input_ids
         if len(kw) > 1 and kw[0] == self.tokenizer.bos_token_id:
             kw = kw[1:]
         reqs = []
-        for image, question in zip(images, questions):
+        for k, (image, question) in enumerate(zip(images, questions)):
             ids = tokenizer_image_object_token(build_prompt_v1(DEFAULT_IMAGE_TOKEN + "\n" + question), self.tokenizer)
-            img, _ = self._pixels(image, None)
+            if originals is not None and self._img_src is not None:
+                img, _ = self.device_pixels(originals[k], None)
+            else:
+                img, _ = self._pixels(image, None)
             reqs.append((ids, img, None, None, None))
         outs = self.engine.generate_batch(reqs, max_new_tokens, self.eos, stop_ids=kw)
         texts = []
