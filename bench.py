@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--no-prefix-cache", action="store_true",
                     help="recompute the K/V rows of the constant text prefix (system prompt before <im_start>) for every crop")
     ap.add_argument("--gemm-l2-hints", type=int, default=-1, help="A/B switch for vsb_gemm_set_l2_hints (-1 = library default)")
+    ap.add_argument("--fuse-rope", type=int, default=-1, help="A/B switch for vsb_llama_set_fuse_rope (-1 = library default)")
     ap.add_argument("--depth", type=int, default=2, help="frontier batches in flight (1 = round-1 style synchronous rounds)")
     return ap.parse_args()
 
@@ -368,6 +369,8 @@ def run_b200(args):
         _lib.call("vsb_attn_set_impl", args.attn_impl)
     if args.gemm_l2_hints >= 0:
         _lib.call("vsb_gemm_set_l2_hints", args.gemm_l2_hints)
+    if args.fuse_rope >= 0:
+        _lib.call("vsb_llama_set_fuse_rope", args.fuse_rope)
     cfg = tiny_config() if args.tiny else VSMConfig()
     t0 = time.time()
 

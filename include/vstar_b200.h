@@ -53,6 +53,16 @@ int vsb_gemm_rowscale_bf16(const void* A, long long lda, const void* W, long lon
                            const void* bias, const void* residual, long long ldr, int epilogue, int rows_per_group, long long group_stride,
                            long long group_offset, const void* rowsq_in, int sq_in_chunks, float eps, void* rowsq_out, long long sq_ld,
                            void* stream);
+/* Fused QKV projection of a Llama layer (HF LlamaAttention q/k/v_proj + apply_rotary_pos_emb, modeling_llama.py:138-168, :199-221):
+ * C = [q | k | v] = A . W^T, optional folded RMSNorm (rowsq_in as above), and rotate-half RoPE applied by the epilogue to the q and k
+ * thirds (head_dim 128; cos/sin tables bf16 [max_pos, 64]; position of row m = positions[m] or pos0 + m % T), so q / k land in the KV
+ * cache already rotated.  Bit-identical to vsb_gemm_bf16 followed by vsb_rope_bf16. */
+int vsb_gemm_qkv_rope_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
+                           int rows_per_group, long long group_stride, long long group_offset, const void* rowsq_in, int sq_in_chunks,
+                           float eps, long long sq_ld, const void* cos_table, const void* sin_table, const void* positions, int T, int pos0,
+                           int head_dim, void* stream);
+/* 1 (default): vsb_llama_layers applies RoPE in the QKV GEMM epilogue (head_dim 128); 0: separate vsb_rope_bf16 launch */
+int vsb_llama_set_fuse_rope(int on);
 /* per-row sum of squares (fp32) of a bf16 matrix: the first rowsq_in of a chain of folded GEMMs (sq_in_chunks = 1) */
 int vsb_rowsq_bf16(const void* x, long long ldx, void* out_f32, int rows, int cols, void* stream);
 /* CUDA-event profiling of every vsb_gemm_bf16 launch (bench.py's roofline leg): begin clears the record; end synchronises

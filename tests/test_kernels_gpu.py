@@ -632,6 +632,7 @@ def test_llama_layers_native_runner(ops):
         return ops.llama_layers(table, nl, x, B, Tn, past, cache, B, Tmax, d, H, inter, 1e-6, cos_t, sin_t, scratch)
 
     outs = []
+    # (the native runner applies RoPE inside the QKV GEMM epilogue - head_dim 128 - while python_stack runs the separate kernel)
     for fn in (python_stack, native_stack):
         cache = torch.zeros(nl, B, Tmax, 3 * d, dtype=BF, device="cuda")
         x0 = rnd(B * 70, d, seed=110).clone()
@@ -643,6 +644,14 @@ def test_llama_layers_native_runner(ops):
     for a, b in zip(outs[0], outs[1]):
         assert torch.equal(a, b)
     assert float(outs[0][0].float().abs().max()) > 0 and torch.isfinite(outs[0][1].float()).all()
+    from vstar_b200 import _lib
+    _lib.call("vsb_llama_set_fuse_rope", 0)                       # and with the fusion switched off: still the same bits
+    try:
+        cache = torch.zeros(nl, B, Tmax, 3 * d, dtype=BF, device="cuda")
+        y0 = native_stack(rnd(B * 70, d, seed=110).clone(), cache, 70, 0)
+        assert torch.equal(y0, outs[0][0])
+    finally:
+        _lib.call("vsb_llama_set_fuse_rope", 1)
     # tail mode: the last layer runs attention / o-proj / MLP over the last rows of every sequence only.  The cache (K/V of
     # every row, every layer) must be bit-identical; the tail rows are bit-identical when the compact GEMMs run on the same
     # tcgen05 kernels as the full pass (more than 16 rows: B * tail = 18) and equal to bf16 rounding when the few rows take

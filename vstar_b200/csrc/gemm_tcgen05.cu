@@ -54,6 +54,12 @@ struct GemmParams {
   long long sq_ld;
   int sq_in_chunks;
   float sq_inv_cols, sq_eps;
+  // rotate-half RoPE applied by the epilogue to the output columns [0, rope_cols) (the q | k thirds of a fused QKV projection,
+  // heads of 128 columns): same bf16 arithmetic as rope_kernel (elementwise.cu) on the same bf16 GEMM results => identical bits
+  const bf16* rope_cos;       // [max_pos][64] bf16
+  const bf16* rope_sin;
+  const int* rope_pos;        // optional position of every A row; else rope_pos0 + m % rope_T
+  int rope_T, rope_pos0, rope_cols;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -443,6 +449,50 @@ __device__ __forceinline__ void epilogue_store_staged(const GemmParams& p, const
   __syncwarp();
 }
 
+// RoPE on one head half pair: a = accumulator columns [j0, j0+32) of a 128-wide head, b = columns [j0+64, j0+96) of the same row.
+// x = bf16(acc * rs) is what the un-fused path stores and rope_kernel reads back; the rotated values are returned as fp32 bit
+// patterns that are exactly representable in bf16 (the store path's rounding is then the identity).
+__device__ __forceinline__ void rope_pair(uint32_t* a, uint32_t* b, float rs, const bf16* __restrict__ cr, const bf16* __restrict__ sr) {
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(cr) + j4);
+    const uint4 s = __ldg(reinterpret_cast<const uint4*>(sr) + j4);
+    const uint32_t cw[4] = {c.x, c.y, c.z, c.w}, sw[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 cs = unpack_bf16x2(cw[q]), sn = unpack_bf16x2(sw[q]);
+      const int j = j4 * 8 + q * 2;
+      const float x1a = rbf(__uint_as_float(a[j]) * rs), x1b = rbf(__uint_as_float(a[j + 1]) * rs);
+      const float x2a = rbf(__uint_as_float(b[j]) * rs), x2b = rbf(__uint_as_float(b[j + 1]) * rs);
+      a[j] = __float_as_uint(rbf(rbf(x1a * cs.x) + rbf(-x2a * sn.x)));
+      a[j + 1] = __float_as_uint(rbf(rbf(x1b * cs.y) + rbf(-x2b * sn.y)));
+      b[j] = __float_as_uint(rbf(rbf(x2a * cs.x) + rbf(x1a * sn.x)));
+      b[j + 1] = __float_as_uint(rbf(rbf(x2b * cs.y) + rbf(x1b * sn.y)));
+    }
+  }
+}
+
+// Epilogue of one warp for a 256-wide q/k tile with fused RoPE: its four 32-column chunks are one 128-wide head; chunk pairs (0,2)
+// and (1,3) are rotated together.  Not inlined: keeps the 64 live accumulator registers out of the common epilogue loop.
+__device__ __noinline__ void rope_epilogue_tile(const GemmParams& p, uint32_t tbase, uint8_t* stage, int m, int m_base, int lane, int n_tile0,
+                                                int chalf, float rs) {
+  const int pos = (m < p.M) ? (p.rope_pos ? p.rope_pos[m] : p.rope_pos0 + (m % p.rope_T)) : 0;
+  const bf16* cr = p.rope_cos + (long long)pos * 64;
+  const bf16* sr = p.rope_sin + (long long)pos * 64;
+  uint4 rdummy[4];
+#pragma unroll 1
+  for (int cc = 0; cc < 2; ++cc) {
+    const int c_lo = chalf * 4 + cc, c_hi = c_lo + 2;
+    uint32_t va[32], vb[32];
+    tmem_ld_32x32(tbase + c_lo * 32, va);
+    tmem_ld_32x32(tbase + c_hi * 32, vb);
+    tmem_ld_wait();
+    rope_pair(va, vb, rs, cr + cc * 32, sr + cc * 32);
+    epilogue_store_staged(p, va, stage, m_base, lane, n_tile0 + c_lo * 32, false, rdummy, 1.f);
+    epilogue_store_staged(p, vb, stage, m_base, lane, n_tile0 + c_hi * 32, false, rdummy, 1.f);
+  }
+}
+
 // 1 / rms of A row m from the partial sums a producer GEMM (or vsb_rowsq_bf16) left behind; fixed summation order
 __device__ __forceinline__ float row_rstd(const GemmParams& p, int m) {
   if (p.rowsq_in == nullptr || m >= p.M) return 1.f;
@@ -567,6 +617,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       if (row_ok) orow = (long long)(m / p.rows_per_group) * p.group_stride + p.group_offset + (m % p.rows_per_group);
       const int c_end = min((chalf + 1) * CPH, BN / 32);
       const int m_base = m_blk * BM + q * 32;
+      if (p.rope_cos != nullptr && n_blk * BN < p.rope_cols) {
+        if constexpr (BN == 256)
+          rope_epilogue_tile(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN), smem + L::EPI_OFFSET + (warp - 4) * EPI_WARP_BYTES,
+                             m, m_base, lane, n_blk * BN, chalf, rs);
+      } else {
       uint4 rnext[4];
       prefetch_residual(p, m_base, lane, n_blk * BN + chalf * CPH * 32, swiglu, rnext);
 #pragma unroll 1
@@ -581,6 +636,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (n0 >= p.N) continue;                      // warp-uniform
         epilogue_store_staged(p, v, smem + L::EPI_OFFSET + (warp - 4) * EPI_WARP_BYTES, m_base, lane, n0, swiglu, rcur, rs);
       }
+      }   // (no fused RoPE on this tile)
       // release this accumulator buffer to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -792,6 +848,11 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       if (row_ok) orow = (long long)(m / p.rows_per_group) * p.group_stride + p.group_offset + (m % p.rows_per_group);
       const int c_end = (chalf + 1) * (BN2 / 64);
       const int m_base = m_blk * 256 + (int)rank * 128 + q * 32;
+      if (p.rope_cos != nullptr && n_blk * BN2 < p.rope_cols) {
+        if constexpr (BN2 == 256)
+          rope_epilogue_tile(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN2), smem + L::EPI_OFFSET + (warp - 4) * EPI_WARP_BYTES,
+                             m, m_base, lane, n_blk * BN2, chalf, rs);
+      } else {
       uint4 rnext[4];
       prefetch_residual(p, m_base, lane, n_blk * BN2 + chalf * (BN2 / 64) * 32, swiglu, rnext);
 #pragma unroll 1
@@ -806,6 +867,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         if (n0 >= p.N) continue;                      // warp-uniform
         epilogue_store_staged(p, v, smem + L::EPI_OFFSET + (warp - 4) * EPI_WARP_BYTES, m_base, lane, n0, swiglu, rcur, rs);
       }
+      }   // (no fused RoPE on this tile)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);     // leader's accumulator-empty barrier
@@ -989,12 +1051,16 @@ extern "C" int vsb_gemm_profile_end(double* flops, double* ms, long long* launch
   return VSB_OK;
 }
 
-struct RowSq {          // folded-RMSNorm side channels of a GEMM (see vsb_gemm_rowscale_bf16)
-  const float* in;
-  float* out;
-  long long ld;
-  int in_chunks;
-  float inv_cols, eps;
+struct RowSq {          // folded-RMSNorm side channels of a GEMM (see vsb_gemm_rowscale_bf16) + fused RoPE (vsb_gemm_qkv_rope_bf16)
+  const float* in = nullptr;
+  float* out = nullptr;
+  long long ld = 0;
+  int in_chunks = 0;
+  float inv_cols = 0.f, eps = 0.f;
+  const bf16* rope_cos = nullptr;
+  const bf16* rope_sin = nullptr;
+  const int* rope_pos = nullptr;
+  int rope_T = 1, rope_pos0 = 0, rope_cols = 0;
 };
 
 static int gemm_dispatch(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
@@ -1037,6 +1103,32 @@ extern "C" int vsb_gemm_rowscale_bf16(const void* A, long long lda, const void* 
   r.inv_cols = 1.f / (float)K;
   r.eps = eps;
   return gemm_profiled(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, epilogue, 0, rows_per_group, group_stride, group_offset, &r,
+                       stream_);
+}
+
+// Fused QKV projection of a Llama layer: C = [q | k | v] = (A . W^T) with optional folded RMSNorm (rowsq_in, as
+// vsb_gemm_rowscale_bf16) and rotate-half RoPE applied by the epilogue to the q and k thirds (columns [0, 2N/3), head_dim 128):
+// the q/k rows land in the KV cache already rotated, vsb_rope_bf16 does not run.  Bit-identical to GEMM followed by vsb_rope_bf16.
+extern "C" int vsb_gemm_qkv_rope_bf16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N,
+                                      int K, int rows_per_group, long long group_stride, long long group_offset, const void* rowsq_in,
+                                      int sq_in_chunks, float eps, long long sq_ld, const void* cos_table, const void* sin_table,
+                                      const void* positions, int T, int pos0, int head_dim, void* stream_) {
+  VSB_CHECK_ARG(cos_table && sin_table && head_dim == 128 && T > 0, "vsb_gemm_qkv_rope_bf16: head_dim must be 128 (got %d)", head_dim);
+  VSB_CHECK_ARG(N % 768 == 0 && ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0, "vsb_gemm_qkv_rope_bf16: N = 3*d with d %% 256 == 0");
+  VSB_CHECK_ARG(!rowsq_in || (sq_in_chunks > 0 && sq_ld >= M), "vsb_gemm_qkv_rope_bf16: bad row statistics");
+  RowSq r;
+  r.in = reinterpret_cast<const float*>(rowsq_in);
+  r.ld = sq_ld;
+  r.in_chunks = sq_in_chunks;
+  r.inv_cols = 1.f / (float)K;
+  r.eps = eps;
+  r.rope_cos = reinterpret_cast<const bf16*>(cos_table);
+  r.rope_sin = reinterpret_cast<const bf16*>(sin_table);
+  r.rope_pos = reinterpret_cast<const int*>(positions);
+  r.rope_T = T;
+  r.rope_pos0 = pos0;
+  r.rope_cols = N / 3 * 2;
+  return gemm_profiled(A, lda, W, ldw, C, ldc, M, N, K, nullptr, nullptr, 0, VSB_EPI_NONE, 0, rows_per_group, group_stride, group_offset, &r,
                        stream_);
 }
 
@@ -1095,6 +1187,12 @@ static int gemm_dispatch(const void* A, long long lda, const void* W, long long 
   p.sq_in_chunks = rsq ? rsq->in_chunks : 0;
   p.sq_inv_cols = rsq ? rsq->inv_cols : 0.f;
   p.sq_eps = rsq ? rsq->eps : 0.f;
+  p.rope_cos = rsq ? rsq->rope_cos : nullptr;
+  p.rope_sin = rsq ? rsq->rope_sin : nullptr;
+  p.rope_pos = rsq ? rsq->rope_pos : nullptr;
+  p.rope_T = rsq ? rsq->rope_T : 1;
+  p.rope_pos0 = rsq ? rsq->rope_pos0 : 0;
+  p.rope_cols = rsq ? rsq->rope_cols : 0;
 
   // decode-sized problems are HBM-bound on W: CUDA-core streaming kernel (gemm_skinny.cu); force_bn = 1 forces it (tests)
   // measured (tools/bench_vqa.py, CUDA-graph timing, fraction of the HBM roofline): FMA kernel 0.57-0.96 at M = 1; mma.sync
@@ -1158,6 +1256,7 @@ static int gemm_dispatch(const void* A, long long lda, const void* W, long long 
     if (r) return r;
     return launch_gemm_2cta(tmA, tmB, p, sms, stream);
   }
+  if (p.rope_cos != nullptr) bn = 256;        // the fused-RoPE epilogue pairs chunks inside one 128-wide head: 256-wide tiles only
   r = make_tensor_map(&tmB, W, N, K, ldw, bn);
   if (r) return r;
   if (bn == 256) return launch_gemm<256>(tmA, tmB, p, sms, stream);

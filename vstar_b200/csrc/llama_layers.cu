@@ -16,6 +16,13 @@ int vsb_flash_attn_tc(const void* q, const void* k, const void* v, void* o, long
                       long long v_bs, long long v_rs, long long o_bs, long long o_rs, int B, int H, int Sq, int Sk, int D, int causal,
                       float scale, cudaStream_t stream);
 
+static int g_fuse_rope = 1;
+// A/B and test switch: 0 = vsb_llama_layers runs RoPE as its own kernel after the QKV projection, 1 (default) = in the GEMM epilogue
+extern "C" int vsb_llama_set_fuse_rope(int on) {
+  g_fuse_rope = on ? 1 : 0;
+  return VSB_OK;
+}
+
 #define VSB_TRY(call)          \
   do {                         \
     int _r = (call);           \
@@ -56,18 +63,28 @@ extern "C" int vsb_llama_layers(const vsb_llama_layer_t* layers, int n_layers, v
     VSB_CHECK_ARG((long long)2 * sqc * rows * 4 <= rows * d * 2, "vsb_llama_layers: scratch too small for the row statistics");
     VSB_TRY(vsb_rowsq_bf16(xb, d, sq_a, (int)rows, d, stream));
   }
+  // RoPE in the QKV epilogue (head_dim 128, tcgen05 path): q / k reach the cache already rotated
+  const bool rope_fused = g_fuse_rope && hd == 128 && d % 256 == 0 && k_start == nullptr && (rows > 16 || vsb_batch_invariant());
   int sq_a_chunks = 1;                                     // layer 0: one full-row sum from vsb_rowsq_bf16
   for (int li = 0; li < n_layers; ++li) {
     const vsb_llama_layer_t& L = layers[li];
     bf16* cl = reinterpret_cast<bf16*>(cache) + (long long)li * Bc * Tmax * ld;       // [Bc*Tmax, 3d]
     if (fused) {
-      VSB_TRY(vsb_gemm_rowscale_bf16(xb, d, L.wqkv, d, cl, ld, (int)rows, 3 * d, d, nullptr, nullptr, 0, VSB_EPI_NONE, Tn, Tmax, past, sq_a,
-                                     sq_a_chunks, rms_eps, nullptr, rows, stream));
+      if (rope_fused)
+        VSB_TRY(vsb_gemm_qkv_rope_bf16(xb, d, L.wqkv, d, cl, ld, (int)rows, 3 * d, d, Tn, Tmax, past, sq_a, sq_a_chunks, rms_eps, rows, rope_cos,
+                                       rope_sin, positions, Tn, past, hd, stream));
+      else
+        VSB_TRY(vsb_gemm_rowscale_bf16(xb, d, L.wqkv, d, cl, ld, (int)rows, 3 * d, d, nullptr, nullptr, 0, VSB_EPI_NONE, Tn, Tmax, past, sq_a,
+                                       sq_a_chunks, rms_eps, nullptr, rows, stream));
     } else {
       VSB_TRY(vsb_rmsnorm_bf16(xb, d, L.ln1, h, d, (int)rows, d, rms_eps, stream));
-      VSB_TRY(vsb_gemm_bf16(h, d, L.wqkv, d, cl, ld, (int)rows, 3 * d, d, nullptr, nullptr, 0, VSB_EPI_NONE, 0, Tn, Tmax, past, stream));
+      if (rope_fused)
+        VSB_TRY(vsb_gemm_qkv_rope_bf16(h, d, L.wqkv, d, cl, ld, (int)rows, 3 * d, d, Tn, Tmax, past, nullptr, 0, rms_eps, rows, rope_cos, rope_sin,
+                                       positions, Tn, past, hd, stream));
+      else
+        VSB_TRY(vsb_gemm_bf16(h, d, L.wqkv, d, cl, ld, (int)rows, 3 * d, d, nullptr, nullptr, 0, VSB_EPI_NONE, 0, Tn, Tmax, past, stream));
     }
-    VSB_TRY(vsb_rope_bf16(cl, ld, (int)rows, Tn, H, hd, past, rope_cos, rope_sin, positions, Tmax, past, stream));
+    if (!rope_fused) VSB_TRY(vsb_rope_bf16(cl, ld, (int)rows, Tn, H, hd, past, rope_cos, rope_sin, positions, Tmax, past, stream));
     if (tail && li == n_layers - 1) {
       const long long trows = (long long)B * tail_rows;
       bf16* xt = attn + trows * d;                                                     // compact copy of the tail rows of x
