@@ -473,8 +473,9 @@ __device__ __forceinline__ void rope_pair(uint32_t* a, uint32_t* b, float rs, co
 }
 
 // Epilogue of one warp for a 256-wide q/k tile with fused RoPE: its four 32-column chunks are one 128-wide head; chunk pairs (0,2)
-// and (1,3) are rotated together.  Not inlined: keeps the 64 live accumulator registers out of the common epilogue loop.
-__device__ __noinline__ void rope_epilogue_tile(const GemmParams& p, uint32_t tbase, uint8_t* stage, int m, int m_base, int lane, int n_tile0,
+// and (1,3) are rotated together.  Only the ROPE instantiations of the kernels (the QKV projection) contain this code, so the
+// register allocation of every other GEMM is untouched.
+__device__ __forceinline__ void rope_epilogue_tile(const GemmParams& p, uint32_t tbase, uint8_t* stage, int m, int m_base, int lane, int n_tile0,
                                                 int chalf, float rs) {
   const int pos = (m < p.M) ? (p.rope_pos ? p.rope_pos[m] : p.rope_pos0 + (m % p.rope_T)) : 0;
   const bf16* cr = p.rope_cos + (long long)pos * 64;
@@ -503,7 +504,7 @@ __device__ __forceinline__ float row_rstd(const GemmParams& p, int m) {
 
 constexpr int GEMM_THREADS = 384;   // warps 0-3: TMA / MMA / TMEM-alloc / spare; warps 4-11: epilogue (2 per TMEM lane quarter)
 
-template <int BN>
+template <int BN, bool ROPE = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using L = SmemLayout<BN>;
@@ -617,8 +618,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       if (row_ok) orow = (long long)(m / p.rows_per_group) * p.group_stride + p.group_offset + (m % p.rows_per_group);
       const int c_end = min((chalf + 1) * CPH, BN / 32);
       const int m_base = m_blk * BM + q * 32;
-      if (p.rope_cos != nullptr && n_blk * BN < p.rope_cols) {
-        if constexpr (BN == 256)
+      if (ROPE && BN == 256 && n_blk * BN < p.rope_cols) {
+        if constexpr (ROPE && BN == 256)
           rope_epilogue_tile(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN), smem + L::EPI_OFFSET + (warp - 4) * EPI_WARP_BYTES,
                              m, m_base, lane, n_blk * BN, chalf, rs);
       } else {
@@ -732,6 +733,7 @@ struct Smem2 {
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
+template <bool ROPE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using L = Smem2;
@@ -848,8 +850,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       if (row_ok) orow = (long long)(m / p.rows_per_group) * p.group_stride + p.group_offset + (m % p.rows_per_group);
       const int c_end = (chalf + 1) * (BN2 / 64);
       const int m_base = m_blk * 256 + (int)rank * 128 + q * 32;
-      if (p.rope_cos != nullptr && n_blk * BN2 < p.rope_cols) {
-        if constexpr (BN2 == 256)
+      if (ROPE && n_blk * BN2 < p.rope_cols) {
+        if constexpr (ROPE)
           rope_epilogue_tile(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN2), smem + L::EPI_OFFSET + (warp - 4) * EPI_WARP_BYTES,
                              m, m_base, lane, n_blk * BN2, chalf, rs);
       } else {
@@ -957,27 +959,28 @@ int make_tensor_map(CUtensorMap* out, const void* ptr, long long rows, long long
   return VSB_OK;
 }
 
-template <int BN>
+template <int BN, bool ROPE = false>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int max_ctas, cudaStream_t stream) {
   using L = SmemLayout<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    VSB_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    VSB_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, ROPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
   p.tiles_m = (p.M + BM - 1) / BM;
   p.tiles_n = (p.N + BN - 1) / BN;
   int tiles = p.tiles_m * p.tiles_n;
   int grid = tiles < max_ctas ? tiles : max_ctas;
-  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p);
+  gemm_bf16_tcgen05_kernel<BN, ROPE><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p);
   VSB_LAUNCH_CHECK();
   return VSB_OK;
 }
 
+template <bool ROPE>
 int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int max_ctas, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    VSB_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::TOTAL));
+    VSB_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<ROPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::TOTAL));
     attr_set = true;
   }
   p.tiles_m = (p.M + 255) / 256;
@@ -986,7 +989,7 @@ int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams&
   int clusters = max_ctas / 2;
   if (clusters > tiles) clusters = tiles;
   if (clusters < 1) clusters = 1;
-  gemm_bf16_tcgen05_2cta_kernel<<<2 * clusters, GEMM_THREADS, Smem2::TOTAL, stream>>>(tmA, tmB, p);
+  gemm_bf16_tcgen05_2cta_kernel<ROPE><<<2 * clusters, GEMM_THREADS, Smem2::TOTAL, stream>>>(tmA, tmB, p);
   VSB_LAUNCH_CHECK();
   return VSB_OK;
 }
@@ -1254,12 +1257,12 @@ static int gemm_dispatch(const void* A, long long lda, const void* W, long long 
     p.group_m = g_group_m > 0 ? g_group_m : 16;    // 4096-row bands: measured +2 % over 2048 on the 7B shapes, A band + W still L2-friendly
     r = make_tensor_map(&tmB, W, N, K, ldw, 128);
     if (r) return r;
-    return launch_gemm_2cta(tmA, tmB, p, sms, stream);
+    return p.rope_cos ? launch_gemm_2cta<true>(tmA, tmB, p, sms, stream) : launch_gemm_2cta<false>(tmA, tmB, p, sms, stream);
   }
   if (p.rope_cos != nullptr) bn = 256;        // the fused-RoPE epilogue pairs chunks inside one 128-wide head: 256-wide tiles only
   r = make_tensor_map(&tmB, W, N, K, ldw, bn);
   if (r) return r;
-  if (bn == 256) return launch_gemm<256>(tmA, tmB, p, sms, stream);
+  if (bn == 256) return p.rope_cos ? launch_gemm<256, true>(tmA, tmB, p, sms, stream) : launch_gemm<256>(tmA, tmB, p, sms, stream);
   if (bn == 128) return launch_gemm<128>(tmA, tmB, p, sms, stream);
   if (bn == 32) return launch_gemm<32>(tmA, tmB, p, sms, stream);
   return launch_gemm<64>(tmA, tmB, p, sms, stream);
