@@ -100,6 +100,23 @@ def test_weak_cue_calls_are_batched_across_lockstep_searches():
     assert max(n for _, n in stub.cue_batches) == 3 and {k for k, _ in stub.cue_batches} == {"vqa", "segmentation"}
 
 
+def test_children_of_nodes_under_evaluation_fill_spare_batch_capacity():
+    """a single search with a wide batch: the root goes out together with its four children (their geometry is known before the
+    root commits), so the 1 + 4 + 16 + 64 tree needs 3 GPU rounds instead of 4 - and walks the same trajectory"""
+    g = np.load(os.path.join(G, "search_stub_3lvl.npz"))
+    img = synth_image(int(g["img_seed"]), int(g["w"]), int(g["h"]))
+    kw = json.loads(str(g["kw"]))
+    runs = {}
+    for spec in (True, False):
+        stub = RecordStub()
+        st = VS.SearchState(img, "mug", int(g["smallest"]), **kw)
+        ctl = VS.SearchController(stub, NumpyScorer(), 128, depth=1, speculate_children=spec)
+        ctl.run([st])
+        assert np.array_equal(np.array([s["bbox"] for s in st.search_path]), g["trajectory"])
+        runs[spec] = list(stub.batches)
+    assert runs[True][0] == 5 and runs[False][0] == 1 and len(runs[True]) < len(runs[False])
+
+
 def test_more_than_16_valid_boxes_at_the_root():
     """all_valid_boxes when the record's 16 slots overflow: fetched from the owner, equal to the map-based path"""
     img = synth_image(24, 1280, 960)
