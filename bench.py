@@ -613,7 +613,36 @@ def run_b200(args):
             e1.record()
             torch.cuda.synchronize()
             ms_w = e0.elapsed_time(e1)
-            out["weak_cue"] = {"workload": f"{sw} lock-step searches of 1024x1024 images (root + 4 crops) whose ROOT takes the context-cue branch: "
+            # the same with FREE-RUNNING cue answers (no forced ids): batched exact greedy decoding of 24 tokens per weak node
+            free_vsm = BenchVSM(engine=engine, frontier_batch=args.batch)
+            free_vsm.vqa_max_new_tokens = 24
+            free_vsm.draft_ids, free_vsm.forced_answer_ids = vsm.draft_ids, None
+
+            class CueVSM:          # detections through the forced-answer VSM (random weights never emit [LOC]), cue calls unforced
+                frontier_batch = args.batch
+
+                def __getattr__(self, name):
+                    return getattr(vsm, name)
+
+                def inference_many(self, regions, questions, mode):
+                    return (free_vsm if mode == "vqa" else vsm).inference_many(regions, questions, mode)
+
+            def wstep_free():
+                from vstar_b200.visual_search import SearchController, SearchState
+                states = [SearchState(img, name, ss, **kw_weak) for img, name, ss in w_jobs]
+                SearchController(CueVSM(), None, args.batch, depth=args.depth).run(states)
+                return sum(st.n_evals for st in states)
+
+            wstep_free()
+            torch.cuda.synchronize()
+            t_free = time.perf_counter()
+            det_free = wstep_free()
+            torch.cuda.synchronize()
+            t_free = time.perf_counter() - t_free
+            out["weak_cue"] = {"free_running_cue_answers": {"crops_per_s": det_free / t_free, "ms_per_step": t_free * 1e3,
+                                                            "what": "cue answers decoded greedily (24 new tokens, VSMEngine.generate_many: one "
+                                                                    "batched prefill + one decode step per token for all weak nodes of a round)"},
+                               "workload": f"{sw} lock-step searches of 1024x1024 images (root + 4 crops) whose ROOT takes the context-cue branch: "
                                            "5 detection evaluations + 1 'vqa' + 1 'segmentation' model call per search, the cue calls batched "
                                            "across the searches (synthetic forced answer, so no free-running decode)",
                                "crops_per_s": det / (ms_w / 1e3), "model_calls_per_s": (det + 2 * sw * n_w) / (ms_w / 1e3),

@@ -191,27 +191,46 @@ def test_vsm_inference_api_modes(tiny_vsm):
     assert abs(evs[0].top_logit - float(scores.max())) < 2e-2
 
 
-def test_draft_mismatch_falls_back_to_exact_greedy(tiny_vsm):
-    """without forcing, random weights do not emit the draft -> per-crop exact greedy decode path"""
+def test_free_form_answers_are_exact_greedy_and_batched(tiny_vsm):
+    """mode='vqa' without a forced answer (the cue question of the weak-cue branch): batched exact greedy decoding on the KV cache
+    (VSMEngine.generate_many) - every emitted token is the fp32 oracle's (use_cache=False) argmax along the emitted path up to
+    the bf16 logit tolerance (random weights give near-flat logits, so near-ties may resolve either way); a detection-mode crop
+    whose greedy answer deviates from the draft falls back to per-crop exact greedy decoding"""
     from vstar_b200.vsm import VSM
     vsm, O, cfg, sd = tiny_vsm
-    free = VSM(engine=vsm.engine, frontier_batch=2)
+    free = VSM(engine=vsm.engine, frontier_batch=4)
     free._ids = vsm._ids
-    img = synth_image(79, 128, 128)
-    text = free.inference(img, "q", mode="vqa")
+    free.vqa_max_new_tokens = 5
+    imgs = [synth_image(79 + k, 128 + 8 * k, 128) for k in range(3)]
+    text = free.inference(imgs[0], "q", mode="vqa")
     assert isinstance(text, str)
-    assert free.engine.stats["fallback"] >= 1
-    # exact-greedy semantics: every emitted token must be the oracle's (fp32, use_cache=False) argmax at that step, up
-    # to bf16 logit tolerance (random weights give near-flat logits, so near-ties are allowed to resolve either way)
+    texts = free.inference_many([(im, [0, 0, im.width, im.height]) for im in imgs], ["q"] * 3, "vqa")
+    assert len(texts) == 3 and all(isinstance(t, str) for t in texts)
     prompt = torch.tensor([vsm._ids("q")])
-    ic = O.preprocess_clip(img)
-    out, am2 = free.engine.generate(prompt, ic.to(BF).cuda(), max_new_tokens=6, eos_token_id=2)
+    ics = torch.cat([O.preprocess_clip(im) for im in imgs])
+    outs = free.engine.generate_many(prompt.expand(3, -1).contiguous(), ics.to(BF).cuda(), max_new_tokens=5, eos_token_id=2)
+    for b in range(3):
+        ids = prompt.clone()
+        for t in outs[b][prompt.shape[1]:]:
+            logits, _ = O.lm_forward(sd, cfg, ids, ics[b:b + 1])
+            last = logits[0, -1]
+            assert float(last.max() - last[t]) < 3e-2, (b, t, int(last.argmax()), float(last.max() - last[t]))
+            ids = torch.cat([ids, torch.tensor([[t]])], dim=1)
+    # single-sequence path (used by the draft-verify fallback): same property
+    out, am2 = free.engine.generate(prompt, ics[:1].to(BF).cuda(), max_new_tokens=6, eos_token_id=2)
     ids = prompt.clone()
     for t in am2:
-        logits, _ = O.lm_forward(sd, cfg, ids, ic)
+        logits, _ = O.lm_forward(sd, cfg, ids, ics[:1])
         last = logits[0, -1]
         assert float(last.max() - last[t]) < 3e-2, (t, int(last.argmax()), float(last.max() - last[t]))
         ids = torch.cat([ids, torch.tensor([[t]])], dim=1)
+    # detection mode, unforced: random weights do not emit the draft -> fallback counted (and, with no [LOC], the reference's error)
+    n0 = free.engine.stats["fallback"]
+    try:
+        free.inference(imgs[0], "q", mode="detection")
+    except RuntimeError as e:
+        assert "[LOC]" in str(e)
+    assert free.engine.stats["fallback"] >= n0 + 1
 
 
 def test_vsmforcausallm_mirror_api(tiny_vsm):

@@ -700,6 +700,32 @@ class VSMEngine(LlamaClipCore):
         self._graphs[key] = ent
         return ent
 
+    def generate_many(self, prompt_ids, images_clip, max_new_tokens=100, eos_token_id=2):
+        """Exact greedy decoding for B crops that share one prompt LENGTH (the cue question of the weak-cue branch asked of many
+        crops, visual_search.py:427-431): ONE batched prefill, then one decode step per token for the whole batch (every weight
+        byte read once for B tokens); sequences that have emitted EOS keep stepping and are ignored.
+        -> list of B token-id lists (prompt + answer incl. EOS), like `generate` gives for one crop."""
+        c = self.cfg
+        B, L = prompt_ids.shape
+        room = self.MAX_POSITIONS - (L - 1 + c.clip_tokens)
+        x, T, img_pos = self.prefill(prompt_ids.cpu(), images_clip, reserve=max(0, min(max_new_tokens, room)))
+        last = self._const(("rows", tuple(self.x_row(b, T - 1) for b in range(B))), [self.x_row(b, T - 1) for b in range(B)])
+        hn, am, logits = self._logits_rows(x, last)
+        outs = [prompt_ids[b].cpu().tolist() for b in range(B)]
+        done = [False] * B
+        past = T
+        for step in range(max_new_tokens):
+            nxt = am.cpu().tolist()                       # one D2H per step for the whole batch
+            for b in range(B):
+                if not done[b]:
+                    outs[b].append(int(nxt[b]))
+                    done[b] = int(nxt[b]) == eos_token_id
+            if all(done) or step == max_new_tokens - 1:
+                break
+            am, hn, logits = self.decode_step(torch.tensor(nxt, dtype=torch.int64, device=self.dev), B, past)
+            past += 1
+        return outs
+
     def generate(self, prompt_ids, images_clip, max_new_tokens=100, eos_token_id=2, forced_ids=None):
         """Exact greedy decoding for ONE sequence on the fused-QKV cache (reference: HF generate, use_cache=False —
         mathematically the same sequence).  Returns (output_ids list, per-step argmax list, residual rows)."""

@@ -206,6 +206,7 @@ class VSM:
         self.upload_chunk = int(os.environ.get("VSB_UPLOAD_CHUNK", "16"))
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.vqa_max_new_tokens = 100          # max_new_tokens of VSM.inference(mode='vqa') (visual_search.py:201)
         self._host_pool = {}
         self._d2h_stream = None
 
@@ -329,6 +330,14 @@ class VSM:
                 t1 = time.perf_counter()
                 self.timers["prep"] += t1 - t0
                 prompt = torch.tensor([ids_list[i] for i in chunk], dtype=torch.int64)
+                if mode == "vqa" and self.forced_answer_ids is None:
+                    # free-form answer (the cue question): nothing to draft-verify - batched exact greedy decoding
+                    toks = self.engine.generate_many(prompt, ic, max_new_tokens=self.vqa_max_new_tokens, eos_token_id=self.eos)
+                    out = dict(output_ids=[torch.tensor(t) for t in toks], verified=[True] * len(chunk), n_crops=len(chunk))
+                    pend["chunks"].append([chunk, out, io, ic, prompt, None])
+                    t0 = time.perf_counter()
+                    self.timers["engine"] += t0 - t1
+                    continue
                 out = self.engine.inference(io, ic, prompt, self.draft_ids, eos_token_id=self.eos, mode=mode,
                                             forced_ids=self.forced_answer_ids, defer=True)
                 if rec is not None:
