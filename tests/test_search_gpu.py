@@ -154,6 +154,32 @@ def test_pipelined_records_equal_synchronous_maps(tiny_vsm):
     assert hb.shape == (520, 700, 1) and hb.dtype == np.float32 and float(hb.max()) == 1.0 and float(hb.min()) == 0.0
 
 
+def test_weak_cue_branch_batched_equals_one_call_at_a_time(tiny_vsm):
+    """context-cue branch on the CUDA VSM (visual_search.py:427-443): three lock-step searches whose every expandable node takes it -
+    cue answers and cue segmentations go out as batches (VSM.inference_many) - against the same engine driven through the
+    reference-style API, one inference() call at a time with materialised heat maps: identical trajectories, cue strings and
+    queue priorities"""
+    from vstar_b200 import visual_search as VS
+    vsm, O, cfg, sd = tiny_vsm
+    kw = dict(confidence_high=2.0, target_cue_threshold=1e9, target_cue_threshold_minimum=1e9)
+    imgs = [synth_image(120 + k, 420 + 16 * k, 400) for k in range(3)]
+
+    class OneByOne:
+        def inference(self, image, question, mode="segmentation"):
+            return vsm.inference(image, question, mode)
+
+    ref = [VS.visual_search(OneByOne(), im, "mug", None, 150, return_state=True, **kw)[4] for im in imgs]
+    ctl = VS.SearchController(vsm, None, 16)
+    states = [VS.SearchState(im, "mug", 150, **kw) for im in imgs]
+    ctl.run(states)
+    assert any(n > 1 for _, n in ctl.cue_batches) and {k for k, _ in ctl.cue_batches} == {"vqa", "segmentation"}
+    for a, b in zip(ref, states):
+        assert [tuple(s["bbox"]) for s in a.search_path] == [tuple(s["bbox"]) for s in b.search_path]
+        assert [s.get("context_cue") for s in a.search_path] == [s.get("context_cue") for s in b.search_path]
+        assert all("context_cue" in s for s in b.search_path if min(s["bbox"][2], s["bbox"][3]) > 150)
+        assert [s["score"] for s in a.search_path[1:]] == [s["score"] for s in b.search_path[1:]]
+
+
 def test_crop_records_do_not_depend_on_the_batch(tiny_vsm):
     """a crop's record is a pure function of the crop: evaluated alone, in a batch of 3 or in a batch of 8 it comes back
     bit-identical (batch-invariant kernels) - the property that lets every rank of a sharded frontier, and every speculative
