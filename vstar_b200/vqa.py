@@ -210,7 +210,8 @@ class VQAEngine(LlamaClipCore):
     def prefill_ragged(self, xs, reserve=0):
         """xs: list of [T_b, d] input embeddings (consumed).  Sequences are LEFT-padded in the shared cache: sequence b
         occupies cache rows [Tpad - T_b, Tpad) of batch slot b, so every sequence ends at the same row and one decode
-        step is ONE set of kernels for the whole batch (each weight byte read once for B tokens).
+        step is ONE set of kernels for the whole batch (each weight byte read once for B tokens).  Runs of neighbouring
+        sequences of EQUAL length are prefilled as one batch (M = G * T rows) - generate_batch orders its requests by length.
         -> (last-position logits fp32 [B, V], Tpad, lengths)"""
         B = len(xs)
         lens = [int(x.shape[0]) for x in xs]
@@ -219,9 +220,16 @@ class VQAEngine(LlamaClipCore):
         self._prefix_slots = 0
         Tm = self._cache_shape[2]
         last = []
-        for b, x in enumerate(xs):
-            self._llm_layers(x, 1, lens[b], 0, Tm, cache_row_offset=b * Tm + (Tpad - lens[b]))
-            last.append(x[-1:])
+        b = 0
+        while b < B:
+            G = 1
+            while b + G < B and lens[b + G] == lens[b]:
+                G += 1
+            T = lens[b]
+            x = torch.cat(xs[b:b + G], 0).contiguous() if G > 1 else xs[b]
+            self._llm_layers(x, G, T, 0, Tm, cache_row_offset=b * Tm + (Tpad - T))
+            last += [x[g * T + T - 1:g * T + T] for g in range(G)]
+            b += G
         self.kv_epoch = getattr(self, "kv_epoch", 0) + 1
         hn = ops.rmsnorm(torch.cat(last, 0).contiguous(), self.w.final_norm, self.cfg.rms_eps)
         return ops.gemm(hn, self.w.lm_head, out_dtype=torch.float32), Tpad, lens
@@ -243,7 +251,9 @@ class VQAEngine(LlamaClipCore):
         """greedy generation for several (input_ids, image, object_crops, images_long, objects_long) requests at once.
         Same per-sequence semantics as generate(); finished sequences idle (their slots keep stepping, results ignored).
         -> list of new-token lists"""
-        xs = [self.build_embeds(ids, img, crops, il, ol) for ids, img, crops, il, ol in requests]
+        xs = self.build_embeds_batch(list(requests))           # one CLIP + projector pass for every image of the batch
+        perm = sorted(range(len(xs)), key=lambda i: int(xs[i].shape[0]))       # equal lengths next to each other (stable)
+        xs = [xs[i] for i in perm]
         longest = max(int(x.shape[0]) for x in xs)
         logits, Tpad, lens = self.prefill_ragged(xs, reserve=max(0, min(max_new_tokens, self.MAX_POSITIONS - longest)))
         B = len(xs)
@@ -260,7 +270,10 @@ class VQAEngine(LlamaClipCore):
             if all(done) or step == max_new_tokens - 1:
                 break
             logits = self.decode_ragged(nxt, lens, Tpad, step)
-        return outs
+        res = [None] * B
+        for k, i in enumerate(perm):
+            res[i] = outs[k]
+        return res
 
     def option_losses(self, question_ids, options_ids, image, object_crops=None, images_long=None, objects_long=None):
         """multiple_choices_inference core (vstar_bench_eval.py:127-163).  Returns (losses fp32 [n_options] on host, argmin)."""
