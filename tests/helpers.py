@@ -100,17 +100,19 @@ class StubVSM:
 
 
 def pack_record_numpy(boxes, logits, low, bbox, smallest, R):
-    """TEST-side restatement of the crop-record layout (vstar_b200/records.py, csrc/heads.cu) with numpy"""
+    """TEST-side restatement of the crop-record layout (vstar_b200/records.py, csrc/heads.cu) with numpy; logits None = the
+    record of a cue segmentation (heat-map part only)"""
     from vstar_b200 import records as RC
     row = np.zeros(R, np.float32)
-    sc = logits.view(-1).numpy()
-    ti = int(sc.argmax())
-    row[RC.REC_TOP], row[RC.REC_BOX:RC.REC_BOX + 4] = sc[ti], boxes[ti].numpy()
-    row[RC.REC_NROWS], row[RC.REC_TOPIDX] = len(sc), ti
-    valid = np.nonzero(sc > 0.5)[0]
-    row[RC.REC_NVALID] = len(valid)
-    for k, vi in enumerate(valid[:RC.REC_MAXVALID]):
-        row[RC.REC_VALID + 4 * k:RC.REC_VALID + 4 * k + 4] = boxes[vi].numpy()
+    if logits is not None:
+        sc = logits.view(-1).numpy()
+        ti = int(sc.argmax())
+        row[RC.REC_TOP], row[RC.REC_BOX:RC.REC_BOX + 4] = sc[ti], boxes[ti].numpy()
+        row[RC.REC_NROWS], row[RC.REC_TOPIDX] = len(sc), ti
+        valid = np.nonzero(sc > 0.5)[0]
+        row[RC.REC_NVALID] = len(valid)
+        for k, vi in enumerate(valid[:RC.REC_MAXVALID]):
+            row[RC.REC_VALID + 4 * k:RC.REC_VALID + 4 * k + 4] = boxes[vi].numpy()
     rects = RC.pyramid_rects(bbox, smallest)
     if rects:
         heat = NumpyScorer().from_low_res(torch.from_numpy(low), int(bbox[3]), int(bbox[2]))
@@ -130,7 +132,9 @@ class RecordStub(StubVSM):
         self.n_local = 0
         self.batches = []
 
-    def detect_regions_launch(self, regions, questions, smallest_sizes, rec_len=None):
+    cue_records = True
+
+    def detect_regions_launch(self, regions, questions, smallest_sizes, rec_len=None, mode="detection"):
         from vstar_b200 import records as RC
         R = max(rec_len or 0, RC.record_floats(max(len(RC.pyramid_rects(b, ss)) for (_, b), ss in zip(regions, smallest_sizes))))
         rec = torch.zeros((len(regions), R), dtype=torch.float32)
@@ -139,7 +143,7 @@ class RecordStub(StubVSM):
         for k, ((src, b), q, ss) in enumerate(zip(regions, questions, smallest_sizes)):
             self.n_local += 1
             im = src.crop((int(b[0]), int(b[1]), int(b[0] + b[2]), int(b[1] + b[3])))
-            _, boxes, logits, low = self._eval(im, q, "detection")
+            _, boxes, logits, low = self._eval(im, q, mode)
             rec[k] = torch.from_numpy(pack_record_numpy(boxes, logits, low, b, ss, R))
             keep.append((boxes, logits, torch.from_numpy(low)))
         return dict(rec=rec, keep=keep, regions=regions, smallest=list(smallest_sizes))
@@ -150,7 +154,8 @@ class RecordStub(StubVSM):
         for k, (boxes, logits, low) in enumerate(h["keep"]):
             ev = _NodeEval.from_record(h["rec"][k].numpy(), h["regions"][k][1], h["smallest"][k])
             ev.low_res, ev.boxes, ev.scores = low, boxes, logits
-            ev.fetch_valid = (lambda b=boxes, s=logits: b[s.view(-1) > 0.5].view(-1, 4))
+            if logits is not None:
+                ev.fetch_valid = (lambda b=boxes, s=logits: b[s.view(-1) > 0.5].view(-1, 4))
             out.append(ev)
         return out
 
@@ -159,8 +164,10 @@ class RecordStub(StubVSM):
             smallest_sizes = [max(1, min(int(b[2]), int(b[3])) // 2) for _, b in regions]
         return self.detect_regions_finish(self.detect_regions_launch(regions, questions, smallest_sizes))
 
-    def inference_many(self, regions, questions, mode):
+    def inference_many(self, regions, questions, mode, smallest_sizes=None):
         self.cue_batches = getattr(self, "cue_batches", []) + [(mode, len(regions))]
+        if mode == "segmentation" and smallest_sizes is not None:         # cue maps as crop records, like the CUDA VSM
+            return self.detect_regions_finish(self.detect_regions_launch(regions, questions, smallest_sizes, mode="segmentation"))
         return [self.inference(src.crop((int(b[0]), int(b[1]), int(b[0] + b[2]), int(b[1] + b[3]))), q, mode) for (src, b), q in zip(regions, questions)]
 
 

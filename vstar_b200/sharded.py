@@ -40,10 +40,28 @@ class ShardedVSM:
     def inference(self, image, question, mode="segmentation"):
         return self.vsm.inference(image, question, mode)
 
-    def inference_many(self, regions, questions, mode):
+    cue_records = True
+
+    def inference_many(self, regions, questions, mode, smallest_sizes=None):
+        """weak-cue calls of all parked searches, dealt over the ranks like a frontier batch: cue answers ('vqa') come back as
+        strings through one all_gather_object, cue segmentations as crop records through the same all-gather as detections"""
+        n, w, r = len(regions), self.world, self.rank
+        if mode == "segmentation" and smallest_sizes is not None and getattr(self.vsm, "cue_records", False):
+            return self.detect_regions_finish(self.detect_regions_launch(regions, questions, smallest_sizes, mode="segmentation"))
+        mine = list(range(r, n, w))
         if hasattr(self.vsm, "inference_many"):
-            return self.vsm.inference_many(regions, questions, mode)
-        return [self.vsm.inference(src.crop((int(b[0]), int(b[1]), int(b[0] + b[2]), int(b[1] + b[3]))), q, mode) for (src, b), q in zip(regions, questions)]
+            local = self.vsm.inference_many([regions[i] for i in mine], [questions[i] for i in mine], mode) if mine else []
+        else:
+            local = [self.vsm.inference(regions[i][0].crop((int(regions[i][1][0]), int(regions[i][1][1]), int(regions[i][1][0] + regions[i][1][2]),
+                                                            int(regions[i][1][1] + regions[i][1][3]))), questions[i], mode) for i in mine]
+        if mode != "vqa":
+            # maps cannot travel as objects: without the record interface every rank evaluates every cue segmentation itself
+            if hasattr(self.vsm, "inference_many"):
+                return self.vsm.inference_many(regions, questions, mode)
+            return [self.vsm.inference(src.crop((int(b[0]), int(b[1]), int(b[0] + b[2]), int(b[1] + b[3]))), q, mode) for (src, b), q in zip(regions, questions)]
+        parts = [None] * w
+        dist.all_gather_object(parts, local, group=self.group)
+        return [parts[i % w][i // w] for i in range(n)]
 
     def _buffer(self, name, shape, dtype, pinned=False):
         key = (name, tuple(shape), dtype)
@@ -56,14 +74,15 @@ class ShardedVSM:
             self._bufs[key] = b
         return b
 
-    def detect_regions_launch(self, regions, questions, smallest_sizes):
+    def detect_regions_launch(self, regions, questions, smallest_sizes, mode="detection"):
         n, w, r = len(regions), self.world, self.rank
         mine = list(range(r, n, w))
         n_max = (n + w - 1) // w
         # the record length is a function of the batch's geometry only, so every rank computes the same value
         R = record_floats(max(len(pyramid_rects(b, ss)) for (_, b), ss in zip(regions, smallest_sizes)))
+        kw = {} if mode == "detection" else {"mode": mode}
         local = self.vsm.detect_regions_launch([regions[i] for i in mine], [questions[i] for i in mine],
-                                               [smallest_sizes[i] for i in mine], rec_len=R) if mine else None
+                                               [smallest_sizes[i] for i in mine], rec_len=R, **kw) if mine else None
         cuda = torch.device(self.device).type == "cuda"
         # double-buffered by launch parity: with two batches in flight the previous gather's buffers are still being read
         slot = self.gathers % 4

@@ -258,7 +258,7 @@ class _NodeEval:
     @classmethod
     def from_record(cls, row, bbox, smallest_size):
         r = parse_record(row, bbox, smallest_size)
-        if r["top_index"] < 0:
+        if r["top_index"] < 0 and r["n_logits"] > 0:
             raise RuntimeError("crop evaluation produced no finite detection score (NaN logits)")
         ev = cls()
         ev.top_logit, ev.n_logits, ev.n_valid = r["top_logit"], r["n_logits"], r["n_valid"]
@@ -454,9 +454,13 @@ class SearchController:
             chunks = self.extract_noun_chunks(phrase)
             phrase = chunks[0] if len(chunks) == 1 else "region {}".format(phrase)
             cue = yield ("segmentation", DETECTION_QUESTION.format(phrase))
-            final_heat = cue if isinstance(cue, Heatmap) else self.scorer.from_full_res(cue, h, w)
             st.search_path[idx]["context_cue"] = vqa_results + "#" + phrase
-            pyr = MapPyramid(self.scorer, final_heat, bb)
+            if isinstance(cue, _NodeEval) and cue.pyramid is not None:      # cue map as a crop record (statistics + quad-tree sums)
+                pyr = cue.pyramid
+                final_heat = LazyHeat(self.scorer, cue.low_res, h, w, cue.fetch_low_res)
+            else:
+                final_heat = cue if isinstance(cue, Heatmap) else self.scorer.from_full_res(cue, h, w)
+                pyr = MapPyramid(self.scorer, final_heat, bb)
             terms = chain(pyr)
             fill_pyramids(self.scorer, [(t[0], t[1]) for t in terms])
         st.search_path[idx]["_pyr"] = pyr
@@ -524,7 +528,11 @@ class SearchController:
             if not group:
                 continue
             if hasattr(self.vsm, "inference_many"):
-                replies = self.vsm.inference_many([(st.image, st.current["bbox"]) for st in group], [st.request[1] for st in group], kind)
+                extra = {}
+                if kind == "segmentation" and getattr(self.vsm, "cue_records", False):
+                    extra["smallest_sizes"] = [st.smallest_size for st in group]      # -> cue maps come back as crop records
+                replies = self.vsm.inference_many([(st.image, st.current["bbox"]) for st in group], [st.request[1] for st in group], kind,
+                                                  **extra)
             else:
                 import copy
                 replies = [self.vsm.inference(copy.deepcopy(st.crop(st.current)), st.request[1], mode=kind) for st in group]

@@ -384,24 +384,29 @@ class VSM:
         rec, rects = pend["rec"], pend["rects"]
         col = out["crop_of_loc"]
         B = len(chunk)
-        scores, boxes, low = out["scores"], out["pred_boxes"], out["low_res_masks"]
+        low = out["low_res_masks"]
+        seg_only = pend["mode"] == "segmentation"          # cue segmentation: the record carries the heat-map part only
+        scores = boxes = None
         if col == list(range(B)):
             first = last = list(range(B))
         else:                                   # several [LOC] per answer: pred_boxes[0] / pred_mask[-1] (visual_search.py:208-211)
             first = [col.index(j) for j in range(B)]
             last = [len(col) - 1 - col[::-1].index(j) for j in range(B)]
-            idx = torch.tensor(first, device=scores.device)
-            scores, boxes = scores.index_select(0, idx).contiguous(), boxes.index_select(0, idx).contiguous()
-        if chunk == list(range(chunk[0], chunk[0] + B)):
-            ops.pack_detections(scores.contiguous(), boxes.contiguous(), rec, row0=chunk[0])
-        else:
-            tmp = torch.zeros((B, rec.shape[1]), dtype=torch.float32, device=rec.device)
-            ops.pack_detections(scores.contiguous(), boxes.contiguous(), tmp)
-            rec.index_copy_(0, torch.tensor(chunk, device=rec.device), tmp)
+        if not seg_only:
+            scores, boxes = out["scores"], out["pred_boxes"]
+            if first != list(range(B)):
+                idx = torch.tensor(first, device=scores.device)
+                scores, boxes = scores.index_select(0, idx).contiguous(), boxes.index_select(0, idx).contiguous()
+            if chunk == list(range(chunk[0], chunk[0] + B)):
+                ops.pack_detections(scores.contiguous(), boxes.contiguous(), rec, row0=chunk[0])
+            else:
+                tmp = torch.zeros((B, rec.shape[1]), dtype=torch.float32, device=rec.device)
+                ops.pack_detections(scores.contiguous(), boxes.contiguous(), tmp)
+                rec.index_copy_(0, torch.tensor(chunk, device=rec.device), tmp)
         jobs = []
         for j, i in enumerate(chunk):
             pend["low"][i] = low[last[j]]
-            pend["det"][i] = (scores[j], boxes[j])
+            pend["det"][i] = (scores[j], boxes[j]) if not seg_only else None
             if rects[i]:
                 bb = pend["regions"][i][1]
                 x0, y0 = int(bb[0]), int(bb[1])
@@ -431,7 +436,8 @@ class VSM:
                 results[i] = r
                 continue
             rec1 = torch.zeros((1, rows.shape[1]), dtype=torch.float32, device=self.engine.dev)
-            ops.pack_detections(r["scores"].view(1, -1).contiguous(), r["boxes"].view(1, -1, 4).contiguous(), rec1)
+            if mode != "segmentation":
+                ops.pack_detections(r["scores"].view(1, -1).contiguous(), r["boxes"].view(1, -1, 4).contiguous(), rec1)
             if pend["rects"][i]:
                 bb = pend["regions"][i][1]
                 x0, y0 = int(bb[0]), int(bb[1])
@@ -439,18 +445,20 @@ class VSM:
                                     [(q[0] - x0, q[1] - y0, q[2], q[3]) for q in pend["rects"][i]], 0)], rec1,
                                   r["low_res"].shape[-2], r["low_res"].shape[-1])
             rows[i] = rec1.cpu().numpy()[0]
-            pend["low"][i], pend["det"][i] = r["low_res"], (r["scores"].view(-1), r["boxes"].view(-1, 4))
+            pend["low"][i] = r["low_res"]
+            pend["det"][i] = (r["scores"].view(-1), r["boxes"].view(-1, 4)) if mode != "segmentation" else None
             results[i] = True
         if rows is not None:
             for i in range(n):
                 ev = _NodeEval.from_record(rows[i], pend["regions"][i][1], pend["smallest"][i])
                 ev.low_res = pend["low"][i]
-                ev.scores, ev.boxes = pend["det"][i]
+                if pend["det"][i] is not None:
+                    ev.scores, ev.boxes = pend["det"][i]
 
-                def fetch_valid(sb=pend["det"][i]):
-                    return sb[1][sb[0].view(-1) > 0.5].view(-1, 4).cpu()
+                    def fetch_valid(sb=pend["det"][i]):
+                        return sb[1][sb[0].view(-1) > 0.5].view(-1, 4).cpu()
 
-                ev.fetch_valid = fetch_valid
+                    ev.fetch_valid = fetch_valid
                 results[i] = ev
             rows = None
         for key, buf in pend["host_keys"]:
@@ -509,10 +517,14 @@ class VSM:
         return r["boxes"].cpu(), r["scores"].view(-1, 1).cpu(), heat.map
 
     @torch.inference_mode()
-    def inference_many(self, regions, questions, mode):
+    def inference_many(self, regions, questions, mode, smallest_sizes=None):
         """`inference` for several (search image, bbox) crops in ONE batched engine call - used by the search controller for
         the weak-cue branch of many lock-step searches (visual_search.py:427-443 runs these one node at a time).
-        'vqa' -> list of str; 'segmentation' -> list of Heatmap (clamped H x W map on the GPU + statistics)."""
+        'vqa' -> list of str; 'segmentation' -> list of Heatmap (clamped H x W map on the GPU + statistics), or - when the
+        searches' smallest_sizes are given - list of _NodeEval whose `.pyramid` holds the statistics and quad-tree sums of the cue
+        map (built on the device like the detection records: no H x W map, no per-node host sync)."""
+        if mode == "segmentation" and smallest_sizes is not None:
+            return self._finish(self._launch(regions, questions, "segmentation", smallest=list(smallest_sizes)))
         rs = self._run(regions, questions, mode)
         if mode == "vqa":
             out = []
@@ -528,13 +540,16 @@ class VSM:
         """PIL crops in, see detect_regions"""
         return self.detect_regions([(im, [0, 0, im.width, im.height]) for im in images], questions)
 
+    cue_records = True          # inference_many(mode="segmentation", smallest_sizes=...) answers with crop records (see there)
+
     @torch.inference_mode()
-    def detect_regions_launch(self, regions, questions, smallest_sizes, rec_len=None):
+    def detect_regions_launch(self, regions, questions, smallest_sizes, rec_len=None, mode="detection"):
         """Asynchronous batched detection-mode evaluation for the search controller: regions = [(search image, bbox)].
         smallest_sizes[i] = the search's smallest_size (decides whether crop i will ever be split, i.e. needs the heat-map
         part of its record).  rec_len: record length in floats when the caller needs a common one (sharded frontier: the
-        all-gather wants the same record size on every rank).  Returns a handle for detect_regions_finish."""
-        return self._launch(regions, questions, "detection", smallest=list(smallest_sizes), rec_len=rec_len)
+        all-gather wants the same record size on every rank).  mode="segmentation": the cue segmentation of the weak-cue branch -
+        the record then carries only the heat-map part (statistics + quad-tree sums).  Returns a handle for detect_regions_finish."""
+        return self._launch(regions, questions, mode, smallest=list(smallest_sizes), rec_len=rec_len)
 
     @torch.inference_mode()
     def detect_regions_finish(self, handle):
