@@ -624,8 +624,8 @@ def run_b200(args):
                 def __getattr__(self, name):
                     return getattr(vsm, name)
 
-                def inference_many(self, regions, questions, mode):
-                    return (free_vsm if mode == "vqa" else vsm).inference_many(regions, questions, mode)
+                def inference_many(self, regions, questions, mode, **kw_):
+                    return (free_vsm if mode == "vqa" else vsm).inference_many(regions, questions, mode, **kw_)
 
             def wstep_free():
                 from vstar_b200.visual_search import SearchController, SearchState
