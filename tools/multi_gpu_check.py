@@ -40,6 +40,16 @@ def main():
     t1 = [tuple(s["bbox"]) for s in st.search_path]
     t2 = [tuple(s["bbox"]) for s in st2.search_path]
     same = (t1 == t2) and pl == pl2 and bool(torch.equal(fs["detection_result"], fs2["detection_result"]))
+    # context-cue branch on every expandable node: cue answers travel as strings (all_gather_object), cue maps as crop records
+    from vstar_b200 import noun_chunks
+    noun_chunks.set_nlp(lambda text: [])
+    kw2 = dict(confidence_high=2.0, target_cue_threshold=1e9, target_cue_threshold_minimum=1e9)
+    a = visual_search(vsm, img, "mug", None, 200, return_state=True, **kw2)[4]
+    b = visual_search(sh, img, "mug", None, 200, return_state=True, batch_size=4 * world, **kw2)[4]
+    same_cue = [tuple(s["bbox"]) for s in a.search_path] == [tuple(s["bbox"]) for s in b.search_path] and \
+        [s.get("context_cue") for s in a.search_path] == [s.get("context_cue") for s in b.search_path] and \
+        [s["score"] for s in a.search_path[1:]] == [s["score"] for s in b.search_path[1:]] and any("context_cue" in s for s in b.search_path)
+    same = same and same_cue
     flag = torch.tensor([1 if same else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
