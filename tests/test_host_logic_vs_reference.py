@@ -208,11 +208,37 @@ def check_visualisation_files():
                 assert open(os.path.join(a, f), "rb").read() == open(os.path.join(b, f), "rb").read(), f
 
 
-@pytest.mark.parametrize("name", ["check_visualisation_files", "check_noun_chunks", "check_split_and_sub_patches", "check_refine_bbox_and_iou", "check_prioritize_pop_order_with_ties",
-                                  "check_prompts_and_token_splicing", "check_padding_and_patch_geometry"])
-def test_against_live_reference(name):
-    isolated(name)
+CHECKS = ["check_visualisation_files", "check_noun_chunks", "check_split_and_sub_patches", "check_refine_bbox_and_iou",
+          "check_prioritize_pop_order_with_ties", "check_prompts_and_token_splicing", "check_padding_and_patch_geometry"]
+
+
+@pytest.fixture(scope="module")
+def live_results():
+    """all checks in ONE child process (the import shims patch transformers / torch globally, and importing the reference +
+    transformers costs ~15 s): the child prints one JSON object {check name: "ok" | traceback}"""
+    import json
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "ALL"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert r.returncode == 0 and lines, r.stdout[-2000:] + r.stderr[-4000:]
+    return json.loads(lines[-1])
+
+
+@pytest.mark.parametrize("name", CHECKS)
+def test_against_live_reference(live_results, name):
+    assert live_results.get(name) == "ok", live_results.get(name)
 
 
 if __name__ == "__main__":
-    globals()[sys.argv[1]]()
+    if sys.argv[1] == "ALL":
+        import json
+        import traceback
+        res = {}
+        for name in CHECKS:
+            try:
+                globals()[name]()
+                res[name] = "ok"
+            except Exception:
+                res[name] = traceback.format_exc()[-3000:]
+        print(json.dumps(res))
+    else:
+        globals()[sys.argv[1]]()
